@@ -1,0 +1,17 @@
+"""espnet_b200: B200-native (sm_100a) implementation of ESPnet2's Speech2Text inference hot path.
+
+Public surface mirrors the reference classes on that path:
+Speech2Text, ESPnetASRModel, DefaultFrontend, UtteranceMVN, ConformerEncoder, CTC,
+TransformerDecoder, BatchBeamSearch, Hypothesis, TooShortUttError.
+All compute goes through the C-ABI CUDA library ``libespnet_b200.so`` (include/espnet_b200.h).
+"""
+from .asr_inference import (ESPnetASRModel, Speech2Text, build_model, build_model_from_file, decoder_choices,  # noqa: F401
+                            encoder_choices, frontend_choices, normalize_choices)
+from .ctc import CTC  # noqa: F401
+from .decoder import TransformerDecoder  # noqa: F401
+from .encoder import ConformerEncoder  # noqa: F401
+from .errors import TooShortUttError  # noqa: F401
+from .frontend import DefaultFrontend, LogMel, UtteranceMVN  # noqa: F401
+from .search import BatchBeamSearch, Hypothesis  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,36 @@
+// C-ABI surface shared bits: last-error string, version, GEMM entry point (see include/espnet_b200.h).
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm.h"
+
+static thread_local char g_err[512] = "";
+
+void espb_set_error(const char* msg) {
+  strncpy(g_err, msg ? msg : "", sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+}
+
+extern "C" {
+
+const char* espb_last_error(void) { return g_err; }
+int espb_abi_version(void) { return 1; }
+
+int espb_device_sm(int* major, int* minor) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    espb_set_error("no CUDA device");
+    return ESPB_ERR_CUDA;
+  }
+  *major = prop.major; *minor = prop.minor;
+  return ESPB_OK;
+}
+
+// use_tc = 1: tcgen05 3xTF32 kernel (TMA needs 16-byte aligned strides/bases); 0: SIMT fp32 kernel.
+int espb_gemm_f32(const EspbGemmDesc* d, int use_tc, cudaStream_t stream) {
+  if (!d) { espb_set_error("gemm: null descriptor"); return ESPB_ERR_ARG; }
+  return use_tc ? espb_gemm_tc_launch(*d, stream) : espb_gemm_simt_launch(*d, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,291 @@
+// Warp-primitive kernels of the Conformer encoder: LayerNorm, conv1 of the 2-D subsampling, rel-pos
+// attention glue (q+u / q+v, V transpose, rel-shift + masked softmax) and the convolution module's
+// GLU + depthwise conv + BatchNorm(eval) + Swish.  All outputs that feed a GEMM are written as
+// tf32 hi/lo planes (see gemm.h).
+//
+// Reference: espnet2/legacy/nets/pytorch_backend/transformer/{layer_norm,subsampling,attention}.py,
+// .../conformer/{convolution,encoder_layer}.py (line ranges at each kernel).
+#include "common.cuh"
+
+namespace {
+
+using espb::tf32_hi;
+using espb::tf32_lo;
+
+__device__ __forceinline__ void store_split(float* p, long long plane, float v) {
+  float h = tf32_hi(v);
+  p[0] = h;
+  p[plane] = tf32_lo(v, h);
+}
+
+// ---------------------------------------------------------------- LayerNorm (layer_norm.py:12-42, eps 1e-12)
+// One warp per row, D <= 2048 (D % 32 == 0 not required). out_plain and/or out_split may be null.
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int D, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, float* __restrict__ out_plain,
+                                                        float* __restrict__ out_split, long long split_plane) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * D;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + i * 32;
+    v[i] = (c < D) ? xr[c] : 0.f;
+    s += v[i];
+  }
+  const float mean = espb::warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + i * 32;
+    float d = (c < D) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = 1.0f / sqrtf(espb::warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = lane + i * 32;
+    if (c < D) {
+      float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      if (out_plain) out_plain[row * D + c] = y;
+      if (out_split) store_split(out_split + row * D + c, split_plane, y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- fp32 -> hi/lo planes (weights, pos-emb)
+__global__ void split_kernel(const float* __restrict__ x, long long n, float* __restrict__ out, long long plane) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) store_split(out + i, plane, x[i]);
+}
+
+// ---------------------------------------------------------------- conv1: Conv2d(1, C, 3, stride 2) + ReLU (subsampling.py:400-402)
+// feats [B][Tf_max][F] -> parity-split NHWC planes [B][plane*4 + (t1&1)*2 + (f1&1)][F1h][T1h][C]
+// (hi/lo planes), the layout conv2's implicit GEMM reads with unit-stride TMA boxes.
+__global__ void __launch_bounds__(256) conv1_relu_kernel(const float* __restrict__ feats, int Tf_max, int F, const float* __restrict__ w /*[C][9]*/,
+                                                         const float* __restrict__ bias, int C, float* __restrict__ out, int T1, int F1, int T1h,
+                                                         int F1h) {
+  extern __shared__ float rows[];  // 3 * F input rows
+  const int b = blockIdx.y, t1 = blockIdx.x;
+  const float* in = feats + ((long long)b * Tf_max + 2 * t1) * F;
+  for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) rows[i] = in[i];
+  __syncthreads();
+  const long long sub = (long long)F1h * T1h * C;
+  float* ob = out + (long long)b * 8 * sub;
+  const int pt = t1 & 1, tt = t1 >> 1;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float wk[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) wk[i] = w[c * 9 + i];
+    const float bc = bias[c];
+    for (int f1 = 0; f1 < F1; ++f1) {
+      float acc = bc;
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+        for (int kf = 0; kf < 3; ++kf) acc = fmaf(rows[kt * F + 2 * f1 + kf], wk[kt * 3 + kf], acc);
+      acc = fmaxf(acc, 0.f);
+      const int par = pt * 2 + (f1 & 1), ff = f1 >> 1;
+      float* o = ob + par * sub + ((long long)ff * T1h + tt) * C + c;
+      float h = tf32_hi(acc);
+      o[0] = h;
+      o[4 * sub] = tf32_lo(acc, h);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- attention glue (attention.py:416-459)
+// q (+bias already) lives in the split qkv buffer [M][3D] (hi/lo planes). Writes QU = q+pos_bias_u and QV = q+pos_bias_v as split [M][D].
+__global__ void qu_qv_kernel(const float* __restrict__ qkv, long long qkv_plane, long long M, int D, const float* __restrict__ pos_u,
+                             const float* __restrict__ pos_v, float* __restrict__ qu, float* __restrict__ qv, long long out_plane) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * D) return;
+  long long r = i / D; int c = (int)(i % D);
+  const float* p = qkv + r * 3 * D + c;
+  float q = p[0] + p[qkv_plane];
+  store_split(qu + i, out_plane, q + pos_u[c]);
+  store_split(qv + i, out_plane, q + pos_v[c]);
+}
+
+// V [b][t][h*dk+d] (cols 2D.. of the split qkv buffer) -> VT split [b][h][dk][Tp]; rows t >= len_b are written as 0 so that
+// zero probabilities never meet non-finite padding.
+__global__ void v_transpose_kernel(const float* __restrict__ qkv, long long qkv_plane, int Tmax, int D, int H, const int* __restrict__ lens,
+                                   float* __restrict__ vt, long long vt_plane, int Tp) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z / H, h = blockIdx.z % H, dk = D / H;
+  const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int len = lens[b];
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int t = t0 + i, d = d0 + threadIdx.x;
+    float v = 0.f;
+    if (t < len && d < dk) {
+      const float* p = qkv + ((long long)b * Tmax + t) * 3 * D + 2 * D + h * dk + d;
+      v = p[0] + p[qkv_plane];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int d = d0 + i, t = t0 + threadIdx.x;
+    if (d < dk && t < Tp) store_split(vt + (((long long)b * H + h) * dk + d) * Tp + t, vt_plane, tile[threadIdx.x][i]);
+  }
+}
+
+// scores = (ac[i][j] + bd[i][T-1-i+j]) / sqrt(dk) (rel_shift, attention.py:391-414,455-457); keys j >= len masked
+// (masked_fill(min) -> softmax -> masked_fill(0), attention.py:136-141). One warp per (b,h,i) row. Output split probs [.][Tp].
+__global__ void __launch_bounds__(256) relpos_softmax_kernel(const float* __restrict__ ac, const float* __restrict__ bd, int B, int H, int T, int Tp,
+                                                             int Rp, const int* __restrict__ lens, float inv_scale_div,
+                                                             float* __restrict__ probs, long long probs_plane) {
+  const long long rowid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (rowid >= (long long)B * H * T) return;
+  const int lane = threadIdx.x & 31;
+  const int i = (int)(rowid % T);
+  const int b = (int)(rowid / ((long long)H * T));
+  const int len = lens[b];
+  const float* ar = ac + rowid * Tp;
+  const float* br = bd + rowid * Rp + (T - 1 - i);
+  float* pr = probs + rowid * Tp;
+  float mx = -INFINITY;
+  for (int j = lane; j < len; j += 32) mx = fmaxf(mx, (ar[j] + br[j]) / inv_scale_div);
+  mx = espb::warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < len; j += 32) sum += expf((ar[j] + br[j]) / inv_scale_div - mx);
+  sum = espb::warp_sum(sum);
+  for (int j = lane; j < Tp; j += 32) {
+    float p = 0.f;
+    if (j < len) p = expf((ar[j] + br[j]) / inv_scale_div - mx) / sum;
+    store_split(pr + j, probs_plane, p);
+  }
+}
+
+// ---------------------------------------------------------------- convolution module (convolution.py:56-79)
+// y [M][2C] = pointwise_conv1 output. GLU -> depthwise conv (K taps, zero pad at the utterance's own ends) ->
+// BatchNorm eval folded to x*bn_a + bn_b -> Swish -> split [M][C].
+constexpr int DW_TT = 64, DW_CC = 64;
+__global__ void __launch_bounds__(256) glu_dwconv_bn_swish_kernel(const float* __restrict__ y, int Tmax, int C, const int* __restrict__ lens,
+                                                                  const float* __restrict__ dw_w /*[C][K]*/, const float* __restrict__ dw_b, int K,
+                                                                  const float* __restrict__ bn_a, const float* __restrict__ bn_b,
+                                                                  float* __restrict__ out, long long out_plane) {
+  extern __shared__ float sm[];  // [(DW_TT + K - 1)][DW_CC] GLU'd tile, then [DW_CC][K] weights
+  const int b = blockIdx.z, t0 = blockIdx.x * DW_TT, c0 = blockIdx.y * DW_CC;
+  const int len = lens[b], pad = (K - 1) / 2, rows = DW_TT + K - 1;
+  float* tile = sm;
+  float* wts = sm + rows * DW_CC;
+  for (int i = threadIdx.x; i < rows * DW_CC; i += blockDim.x) {
+    int r = i / DW_CC, c = c0 + (i % DW_CC), t = t0 - pad + r;
+    float v = 0.f;
+    if (t >= 0 && t < len && c < C) {
+      const float* p = y + ((long long)b * Tmax + t) * 2 * C;
+      float a = p[c], g = p[C + c];
+      v = a * (1.f / (1.f + expf(-g)));
+    }
+    tile[i] = v;
+  }
+  for (int i = threadIdx.x; i < DW_CC * K; i += blockDim.x) {
+    int c = c0 + i / K;
+    wts[i] = (c < C) ? dw_w[(long long)c * K + (i % K)] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DW_TT * DW_CC; i += blockDim.x) {
+    int tl = i / DW_CC, cl = i % DW_CC, t = t0 + tl, c = c0 + cl;
+    if (t >= Tmax || c >= C) continue;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(tile[(tl + k) * DW_CC + cl], wts[cl * K + k], acc);
+    acc += dw_b[c];
+    float z = acc * bn_a[c] + bn_b[c];
+    z = espb::swish_acc(z);
+    if (t >= len) z = 0.f;
+    store_split(out + ((long long)b * Tmax + t) * C + c, out_plane, z);
+  }
+}
+
+// x[b, t >= len_b, :] = 0 for plain and split buffers (keeps padded rows finite).
+__global__ void zero_pad_rows_kernel(float* __restrict__ x, int Tmax, int D, const int* __restrict__ lens, long long plane, int nplanes) {
+  const int b = blockIdx.y;
+  const int len = lens[b];
+  long long n = (long long)(Tmax - len) * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float* p = x + ((long long)b * Tmax + len) * D + i;
+    for (int q = 0; q < nplanes; ++q) p[q * plane] = 0.f;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int espb_layernorm_f32(const float* x, long long rows, int D, const float* gamma, const float* beta, float eps, float* out_plain,
+                       float* out_split, long long split_plane, cudaStream_t stream) {
+  if (D > 2048 || D <= 0) { espb_set_error("layernorm: D must be in (0, 2048]"); return ESPB_ERR_ARG; }
+  if (rows <= 0) return ESPB_OK;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (D <= 256) layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+  else if (D <= 512) layernorm_kernel<16><<<grid, 256, 0, stream>>>(x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+  else if (D <= 1024) layernorm_kernel<32><<<grid, 256, 0, stream>>>(x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+  else layernorm_kernel<64><<<grid, 256, 0, stream>>>(x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_split_tf32_f32(const float* x, long long n, float* out, long long plane, cudaStream_t stream) {
+  if (n <= 0) return ESPB_OK;
+  split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, n, out, plane);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_conv1_relu_f32(const float* feats, int B, int Tf_max, int F, const float* w, const float* bias, int C, float* out, int T1, int F1,
+                        int T1h, int F1h, cudaStream_t stream) {
+  if (T1 <= 0 || F1 <= 0) { espb_set_error("conv1: empty output"); return ESPB_ERR_ARG; }
+  dim3 grid(T1, B);
+  conv1_relu_kernel<<<grid, 256, 3 * F * sizeof(float), stream>>>(feats, Tf_max, F, w, bias, C, out, T1, F1, T1h, F1h);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_qu_qv_f32(const float* qkv, long long qkv_plane, long long M, int D, const float* pos_u, const float* pos_v, float* qu, float* qv,
+                   long long out_plane, cudaStream_t stream) {
+  long long n = M * D;
+  qu_qv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(qkv, qkv_plane, M, D, pos_u, pos_v, qu, qv, out_plane);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_v_transpose_f32(const float* qkv, long long qkv_plane, int B, int Tmax, int D, int H, const int* lens, float* vt, long long vt_plane,
+                         int Tp, cudaStream_t stream) {
+  const int dk = D / H;
+  dim3 grid((Tp + 31) / 32, (dk + 31) / 32, B * H), block(32, 8);
+  v_transpose_kernel<<<grid, block, 0, stream>>>(qkv, qkv_plane, Tmax, D, H, lens, vt, vt_plane, Tp);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_relpos_softmax_f32(const float* ac, const float* bd, int B, int H, int T, int Tp, int Rp, const int* lens, float sqrt_dk, float* probs,
+                            long long probs_plane, cudaStream_t stream) {
+  long long rows = (long long)B * H * T;
+  relpos_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_glu_dwconv_bn_swish_f32(const float* y, int B, int Tmax, int C, const int* lens, const float* dw_w, const float* dw_b, int K,
+                                 const float* bn_a, const float* bn_b, float* out, long long out_plane, cudaStream_t stream) {
+  if (K < 1 || (K & 1) == 0 || K > 127) { espb_set_error("dwconv: kernel size must be odd and <= 127"); return ESPB_ERR_ARG; }
+  dim3 grid((Tmax + DW_TT - 1) / DW_TT, (C + DW_CC - 1) / DW_CC, B);
+  size_t smem = ((size_t)(DW_TT + K - 1) * DW_CC + (size_t)DW_CC * K) * sizeof(float);
+  glu_dwconv_bn_swish_kernel<<<grid, 256, smem, stream>>>(y, Tmax, C, lens, dw_w, dw_b, K, bn_a, bn_b, out, out_plane);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_zero_pad_rows_f32(float* x, int B, int Tmax, int D, const int* lens, long long plane, int nplanes, cudaStream_t stream) {
+  dim3 grid(32, B);
+  zero_pad_rows_kernel<<<grid, 256, 0, stream>>>(x, Tmax, D, lens, plane, nplanes);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,431 @@
+// Error-compensated 3xTF32 GEMM on the 5th-gen tensor cores (tcgen05.mma kind::tf32, fp32
+// accumulators in TMEM, operands staged by TMA with 128B swizzle), plus a SIMT fp32 GEMM with the
+// same descriptor (validator for the tensor-core path and path for shapes TMA cannot address).
+//
+// Warp roles per CTA (192 threads, one 128 x BN output tile):
+//   warp 0   : TMA producer (one elected lane)      -> full[s]
+//   warp 1   : TMEM allocator + MMA issuer (one lane) -> empty[s] / tmem_full via tcgen05.commit
+//   warps 2-5: epilogue, TMEM -> registers -> global (bias / activation / residual / hi-lo split)
+#include <cuda.h>
+#include <limits.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "gemm.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                  // 32 fp32 = 128 B = one swizzle row
+constexpr int A_TILE_BYTES = BM * 128;  // one plane
+constexpr int NUM_THREADS = 192;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s watchdog: fail loudly instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: LBO field 1 (unused for swizzled K-major), SBO = 8 rows * 128 B,
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+  uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ shared epilogue
+struct EpiArgs {
+  float* C; long long c_plane, ldc; int split_out;
+  const float* bias; const float* R; long long ldr; float alpha; int act;
+};
+
+__device__ __forceinline__ float epi_value(const EpiArgs& e, float acc, long long row, int col) {
+  float v = acc;
+  if (e.bias) v += __ldg(e.bias + col);
+  v = espb::apply_act_acc(v, e.act);
+  v *= e.alpha;
+  if (e.R) v += e.R[row * e.ldr + col];
+  return v;
+}
+
+// ------------------------------------------------------------------ tensor-core kernel
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym) {
+  constexpr int B_TILE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
+  const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * STAGES, tmem_full_bar = bar_base + 16 * STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 16 * STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int bx = blockIdx.z % p.nbx, by = blockIdx.z / p.nbx;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int cblk = (p.a_mode == 1) ? p.cv_cin / BK : 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        const uint32_t fb = full_bar + 8 * s;
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        if (p.a_mode == 0) {
+          const int ko = (p.kob > 0) ? kb / p.kob : 0;
+          const int ki = (p.kob > 0) ? kb % p.kob : kb;
+          tma_load_5d(sa, &tmA, fb, ki * BK, m0, bx + ko, by, 0);
+          tma_load_5d(sa + A_TILE_BYTES, &tmA, fb, ki * BK, m0, bx + ko, by, 1);
+        } else {  // conv2: tap (kt,kf) of the 3x3/stride-2 window over the parity-split conv1 output
+          const int tap = kb / cblk, c0 = (kb % cblk) * BK;
+          const int kt = tap / 3, kf = tap % 3;
+          const int par = (kt & 1) * 2 + (kf & 1);
+          tma_load_5d(sa, &tmA, fb, c0, m0 + (kt >> 1), bx + (kf >> 1), par, by);
+          tma_load_5d(sa + A_TILE_BYTES, &tmA, fb, c0, m0 + (kt >> 1), bx + (kf >> 1), 4 + par, by);
+        }
+        tma_load_5d(sa + 2 * A_TILE_BYTES, &tmB, fb, kb * BK, n0, bx * bxm, by * bym, 0);
+        tma_load_5d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB, fb, kb * BK, n0, bx * bxm, by * bym, 1);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2 at bits 7,10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar + 8 * s, ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes
+          const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
+          const uint64_t b_hi = umma_desc(sa + 2 * A_TILE_BYTES + k * 32);
+          const uint64_t b_lo = umma_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + k * 32);
+          mma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | k) != 0);  // small terms first
+          mma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+          mma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+        }
+        tcgen05_commit(empty_bar + 8 * s);  // frees the smem stage once these MMAs retire
+      }
+      tcgen05_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    EpiArgs e;
+    const long long coff = (long long)by * p.sc_y + (long long)bx * p.sc_x;
+    e.C = p.C + coff; e.c_plane = p.c_plane; e.ldc = p.ldc; e.split_out = p.split_out;
+    e.bias = p.bias; e.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
+    e.ldr = p.ldr; e.alpha = p.alpha; e.act = p.act;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((coff & 3) == 0) && ((p.c_plane & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      const int col0 = n0 + c * 32;
+      float* crow = e.C + (long long)row * e.ldc;
+      if (!row_ok || col0 >= p.N) {
+        // nothing to store for this lane / column chunk (tile overhang)
+      } else if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o, l;
+          float t0 = epi_value(e, v[j], row, col0 + j), t1 = epi_value(e, v[j + 1], row, col0 + j + 1);
+          float t2 = epi_value(e, v[j + 2], row, col0 + j + 2), t3 = epi_value(e, v[j + 3], row, col0 + j + 3);
+          if (e.split_out) {
+            o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
+            l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
+            *reinterpret_cast<float4*>(crow + col0 + j) = o;
+            *reinterpret_cast<float4*>(crow + e.c_plane + col0 + j) = l;
+          } else {
+            o.x = t0; o.y = t1; o.z = t2; o.w = t3;
+            *reinterpret_cast<float4*>(crow + col0 + j) = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col < p.N) {
+            float t = epi_value(e, v[j], row, col);
+            if (e.split_out) {
+              float h = espb::tf32_hi(t);
+              crow[col] = h; crow[e.c_plane + col] = espb::tf32_lo(t, h);
+            } else {
+              crow[col] = t;
+            }
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ SIMT kernel (fp32 FFMA)
+__device__ __forceinline__ float load_a(const EspbGemmDesc& p, int bx, int by, int m, int k) {
+  if (m >= p.M || k >= p.K) return 0.f;
+  long long off;
+  if (p.a_mode == 0) {
+    int ko = 0, ki = k;
+    if (p.kob > 0) { ko = k / (p.kob * BK); ki = k % (p.kob * BK); }
+    off = (long long)by * p.sa_y + (long long)(bx + ko) * p.sa_x + (long long)m * p.lda + ki;
+    return p.A[off] + p.A[off + p.a_plane];
+  }
+  // conv2 over [b][plane*4 + pt*2 + pf][F1h][T1h][C]
+  const int tap = k / p.cv_cin, c = k % p.cv_cin, kt = tap / 3, kf = tap % 3;
+  const int par = (kt & 1) * 2 + (kf & 1);
+  const int tt = m + (kt >> 1), ff = bx + (kf >> 1);
+  if (tt >= p.cv_t1h || ff >= p.cv_f1h) return 0.f;
+  const long long sub = (long long)p.cv_f1h * p.cv_t1h * p.cv_cin;
+  off = (long long)by * 8 * sub + ((long long)ff * p.cv_t1h + tt) * p.cv_cin + c;
+  return p.A[off + par * sub] + p.A[off + (4 + par) * sub];
+}
+__device__ __forceinline__ float load_b(const EspbGemmDesc& p, int bx, int by, int n, int k) {
+  if (n >= p.N || k >= p.K) return 0.f;
+  long long off = (long long)by * p.sb_y + (long long)bx * p.sb_x + (long long)n * p.ldb + k;
+  return p.B[off] + p.B[off + p.b_plane];
+}
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(EspbGemmDesc p) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int bx = blockIdx.z % p.nbx, by = blockIdx.z / p.nbx;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int r = i >> 4, kk = i & 15;
+      As[kk][r] = load_a(p, bx, by, m0 + r, k0 + kk);
+      Bs[kk][r] = load_b(p, bx, by, n0 + r, k0 + kk);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  EpiArgs e;
+  e.C = p.C + (long long)by * p.sc_y + (long long)bx * p.sc_x; e.c_plane = p.c_plane; e.ldc = p.ldc; e.split_out = p.split_out;
+  e.bias = p.bias; e.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
+  e.ldr = p.ldr; e.alpha = p.alpha; e.act = p.act;
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= p.M) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= p.N) continue;
+      float t = epi_value(e, acc[i][j], row, col);
+      float* c = e.C + (long long)row * e.ldc + col;
+      if (e.split_out) { float h = espb::tf32_hi(t); c[0] = h; c[e.c_plane] = espb::tf32_lo(t, h); }
+      else c[0] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 5-D fp32 tensor map, 128B swizzle, box = {32, box_rows, 1, 1, 1}. strides in elements for dims 1..4.
+int make_map(CUtensorMap* map, const float* base, const long long dims[5], const long long strides_el[4], int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { espb_set_error("cuTensorMapEncodeTiled entry point not available"); return ESPB_ERR_TMA; }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t box[5] = {BK, (cuuint32_t)box_rows, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+  long long packed = 1;
+  for (int i = 0; i < 5; ++i) {
+    gdim[i] = (cuuint64_t)(dims[i] > 0 ? dims[i] : 1);
+  }
+  packed = (long long)gdim[0];
+  for (int i = 0; i < 4; ++i) {
+    long long s = strides_el[i];
+    if (s <= 0) s = ((packed + 3) / 4) * 4;  // unused / broadcast dim (size 1): any legal stride
+    if (s % 4 != 0) { espb_set_error("TMA stride not a multiple of 16 bytes"); return ESPB_ERR_TMA; }
+    gstr[i] = (cuuint64_t)s * 4ull;
+    packed = s * (long long)gdim[i + 1];
+  }
+  if (reinterpret_cast<uintptr_t>(base) & 15) { espb_set_error("TMA base not 16-byte aligned"); return ESPB_ERR_TMA; }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) dims=[%lld,%lld,%lld,%lld,%lld] strides=[%lld,%lld,%lld,%lld]", (int)r,
+             dims[0], dims[1], dims[2], dims[3], dims[4], strides_el[0], strides_el[1], strides_el[2], strides_el[3]);
+    espb_set_error(buf);
+    return ESPB_ERR_TMA;
+  }
+  return ESPB_OK;
+}
+
+template <int BN, int STAGES>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, cudaStream_t stream) {
+  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * BN * 128) + 1024 + 16 * STAGES + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      espb_set_error("cudaFuncSetAttribute(max dynamic smem) failed");
+      return ESPB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.nbx * d.nby);
+  gemm_tf32x3_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+}  // namespace
+
+int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream) {
+  if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.nbx <= 0 || d.nby <= 0) { espb_set_error("gemm: bad shape"); return ESPB_ERR_ARG; }
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (d.a_mode == 0) {
+    long long n_outer = 1, k_inner = d.K;
+    if (d.kob > 0) { k_inner = (long long)d.kob * BK; n_outer = (d.K + k_inner - 1) / k_inner; }
+    long long dims[5] = {k_inner, d.M, d.nbx + n_outer - 1, d.nby, 2};
+    long long str[4] = {d.lda, d.sa_x, d.sa_y, d.a_plane};
+    rc = make_map(&tmA, d.A, dims, str, BM);
+  } else {
+    if (d.cv_cin % BK != 0 || d.K != 9 * d.cv_cin) { espb_set_error("conv2 gemm: cin must be a multiple of 32"); return ESPB_ERR_ARG; }
+    const long long sub = (long long)d.cv_f1h * d.cv_t1h * d.cv_cin;
+    long long dims[5] = {d.cv_cin, d.cv_t1h, d.cv_f1h, 8, d.nby};
+    long long str[4] = {d.cv_cin, (long long)d.cv_t1h * d.cv_cin, sub, 8 * sub};
+    rc = make_map(&tmA, d.A, dims, str, BM);
+  }
+  if (rc != ESPB_OK) return rc;
+  const int bxm = d.sb_x != 0 ? 1 : 0, bym = d.sb_y != 0 ? 1 : 0;
+  const long long tiles_m = (d.M + BM - 1) / BM, nb = (long long)d.nbx * d.nby;
+  int bn;
+  if (d.N <= 64) bn = 64;
+  else if (d.N <= 128) bn = 128;
+  else if (tiles_m * ((d.N + 255) / 256) * nb >= 148) bn = 256;
+  else if (tiles_m * ((d.N + 127) / 128) * nb >= 148) bn = 128;
+  else bn = 64;
+  {
+    long long dims[5] = {d.K, d.N, bxm ? d.nbx : 1, bym ? d.nby : 1, 2};
+    long long str[4] = {d.ldb, d.sb_x, d.sb_y, d.b_plane};
+    rc = make_map(&tmB, d.B, dims, str, bn);
+    if (rc != ESPB_OK) return rc;
+  }
+  if (bn == 256) return launch_tc<256, 2>(tmA, tmB, d, bxm, bym, stream);
+  if (bn == 128) return launch_tc<128, 3>(tmA, tmB, d, bxm, bym, stream);
+  return launch_tc<64, 4>(tmA, tmB, d, bxm, bym, stream);
+}
+
+int espb_gemm_simt_launch(const EspbGemmDesc& d, cudaStream_t stream) {
+  if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.nbx <= 0 || d.nby <= 0) { espb_set_error("gemm: bad shape"); return ESPB_ERR_ARG; }
+  dim3 grid((d.M + 63) / 64, (d.N + 63) / 64, d.nbx * d.nby);
+  gemm_simt_kernel<<<grid, 256, 0, stream>>>(d);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}

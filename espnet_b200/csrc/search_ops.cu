@@ -1,0 +1,547 @@
+// Device-resident joint CTC/attention beam search, batched over utterances (U) x beam slots (W).
+// Slot s = u*W + w.  All hypotheses of a step have the same length, so the step index is a launch
+// argument; per-slot state (scores, CTC forward variables, ancestor table of the self-attention
+// cache) lives in HBM and is double-buffered across steps.
+//
+// Reference semantics: espnet2/legacy/nets/batch_beam_search.py:253-357,359-423 (search, post_process),
+// beam_search.py:385-498 (loop, maxlen/minlen), e2e_asr_common.py:14-44 (end_detect),
+// ctc_prefix_score.py:71-191 + scorers/ctc.py:40-63,101-126 (CTC prefix scorer),
+// asr/decoder/transformer_decoder.py:191-311 + transformer/decoder_layer.py:73-179 (decoder step).
+#include "common.cuh"
+
+namespace {
+
+constexpr float LOGZERO = -10000000000.0f;  // ctc_prefix_score.py:34
+using espb::logaddexp;
+
+__device__ __forceinline__ void store_split(float* p, long long plane, float v) {
+  float h = espb::tf32_hi(v);
+  p[0] = h;
+  p[plane] = espb::tf32_lo(v, h);
+}
+
+// ---------------------------------------------------------------- decoder input: embed(last token)*sqrt(D) + PE[pos]
+__global__ void dec_embed_kernel(const int* __restrict__ last_tok, const float* __restrict__ emb, const float* __restrict__ pe, int pos, int D,
+                                 float scale, float* __restrict__ x) {
+  const int s = blockIdx.x;
+  const float* e = emb + (long long)last_tok[s] * D;
+  const float* p = pe + (long long)pos * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) x[(long long)s * D + c] = e[c] * scale + p[c];
+}
+
+// ---------------------------------------------------------------- self-attention of the newest token over the prefix
+// qkv [n][3D] (this step's q,k,v, bias added). K/V of earlier positions j < pos live in kc/vc [Lmax][n][D] at slot anc[s][j].
+// Writes this step's k,v into kc/vc[pos][s] and ctx (split) [n][D].  One warp per (slot, head); d_k <= 128.
+__global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc,
+                                                            const int* __restrict__ anc, int anc_ld, int n, int D, int H, int pos,
+                                                            float* __restrict__ ctx, long long ctx_plane) {
+  extern __shared__ float sm[];  // per warp: (pos+1) scores
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (wid >= n * H) return;
+  const int s = wid / H, h = wid % H, dk = D / H;
+  float* sc = sm + warp * (pos + 1);
+  const float* q = qkv + (long long)s * 3 * D + h * dk;
+  const float* kn = q + D;
+  const float* vn = q + 2 * D;
+  // append this step's k, v to the cache
+  for (int d = lane; d < dk; d += 32) {
+    kc[((long long)pos * n + s) * D + h * dk + d] = kn[d];
+    vc[((long long)pos * n + s) * D + h * dk + d] = vn[d];
+  }
+  const float rs = sqrtf((float)dk);
+  for (int j = lane; j <= pos; j += 32) {
+    const float* kj = (j == pos) ? kn : kc + ((long long)j * n + anc[(long long)s * anc_ld + j]) * D + h * dk;
+    float a = 0.f;
+    for (int d = 0; d < dk; ++d) a = fmaf(q[d], kj[d], a);
+    sc[j] = a / rs;
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = lane; j <= pos; j += 32) mx = fmaxf(mx, sc[j]);
+  mx = espb::warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j <= pos; j += 32) { float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+  sum = espb::warp_sum(sum);
+  __syncwarp();
+  for (int d = lane; d < dk; d += 32) {
+    float a = 0.f;
+    for (int j = 0; j <= pos; ++j) {
+      const float* vj = (j == pos) ? vn : vc + ((long long)j * n + anc[(long long)s * anc_ld + j]) * D + h * dk;
+      a = fmaf(sc[j] / sum, vj[d], a);
+    }
+    store_split(ctx + (long long)s * D + h * dk + d, ctx_plane, a);
+  }
+}
+
+// ---------------------------------------------------------------- cross-attention of W queries per utterance over the encoder memory
+// q [n][D]; memory K/V: kv + (u*Tmax + t)*kv_ld + k_off / v_off + h*dk.  One block per (utterance, head).
+__global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, long long kv_ld, int k_off,
+                                                           int v_off, int Tmax, const int* __restrict__ lens, int W, int D, int H,
+                                                           float* __restrict__ ctx, long long ctx_plane) {
+  extern __shared__ float sm[];  // q [W][dk] | scores [W][T] | red [4][W][dk]
+  const int u = blockIdx.x / H, h = blockIdx.x % H, dk = D / H;
+  const int T = lens[u];
+  float* qs = sm;
+  float* sc = qs + W * dk;
+  float* red = sc + (long long)W * Tmax;
+  for (int i = threadIdx.x; i < W * dk; i += blockDim.x) qs[i] = q[((long long)(u * W + i / dk)) * D + h * dk + (i % dk)];
+  __syncthreads();
+  const float rs = sqrtf((float)dk);
+  const float* kbase = kv + (long long)u * Tmax * kv_ld + k_off + h * dk;
+  const float* vbase = kv + (long long)u * Tmax * kv_ld + v_off + h * dk;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float* kr = kbase + (long long)t * kv_ld;
+    float a[16];
+#pragma unroll
+    for (int w = 0; w < 16; ++w) a[w] = 0.f;
+    for (int d0 = 0; d0 < dk; d0 += 4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(kr + d0);
+#pragma unroll
+      for (int w = 0; w < 16; ++w) {
+        if (w < W) {
+          const float* qw = qs + w * dk + d0;
+          a[w] = fmaf(qw[0], k4.x, a[w]); a[w] = fmaf(qw[1], k4.y, a[w]);
+          a[w] = fmaf(qw[2], k4.z, a[w]); a[w] = fmaf(qw[3], k4.w, a[w]);
+        }
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < 16; ++w) if (w < W) sc[w * Tmax + t] = a[w] / rs;
+  }
+  __syncthreads();
+  // softmax per slot: one warp per slot (round-robin)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int w = warp; w < W; w += nwarp) {
+    float* r = sc + w * Tmax;
+    float mx = -INFINITY;
+    for (int t = lane; t < T; t += 32) mx = fmaxf(mx, r[t]);
+    mx = espb::warp_max(mx);
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) { float e = expf(r[t] - mx); r[t] = e; sum += e; }
+    sum = espb::warp_sum(sum);
+    for (int t = lane; t < T; t += 32) r[t] = r[t] / sum;
+  }
+  __syncthreads();
+  // ctx[w][d] = sum_t p[w][t] * V[t][d]; thread = (d, t-group)
+  const int ngrp = blockDim.x / dk;  // dk in {16,32,64,128}; blockDim 256 -> >= 2 groups
+  const int d = threadIdx.x % dk, g = threadIdx.x / dk;
+  float acc[16];
+#pragma unroll
+  for (int w = 0; w < 16; ++w) acc[w] = 0.f;
+  if (g < ngrp) {
+    for (int t = g; t < T; t += ngrp) {
+      const float vv = vbase[(long long)t * kv_ld + d];
+#pragma unroll
+      for (int w = 0; w < 16; ++w)
+        if (w < W) acc[w] = fmaf(sc[w * Tmax + t], vv, acc[w]);
+    }
+  }
+  __syncthreads();           // scores no longer needed: reuse `red`
+  if (g < ngrp)
+    for (int w = 0; w < W; ++w) red[((long long)g * W + w) * dk + d] = acc[w];
+  __syncthreads();
+  for (int i = threadIdx.x; i < W * dk; i += blockDim.x) {
+    float a = 0.f;
+    for (int gg = 0; gg < ngrp; ++gg) a += red[(long long)gg * W * dk + i];
+    store_split(ctx + ((long long)(u * W + i / dk)) * D + h * dk + (i % dk), ctx_plane, a);
+  }
+}
+
+// ---------------------------------------------------------------- row-wise top-k (descending; ties -> lower index)
+// vals[r][k], ids[r][k] from x[r][0..V) * scale.  One block per row; k rounds of block arg-max.
+__global__ void __launch_bounds__(256) rows_topk_kernel(const float* __restrict__ x, long long ld, int V, float scale, int k,
+                                                        int* __restrict__ ids, float* __restrict__ vals) {
+  __shared__ float bv[8]; __shared__ int bi[8];
+  __shared__ int chosen[64];
+  const float* r = x + (long long)blockIdx.x * ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int round = 0; round < k; ++round) {
+    float best = -INFINITY; int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+      bool used = false;
+      for (int c = 0; c < round; ++c) used |= (chosen[c] == i);
+      if (used) continue;
+      float v = r[i] * scale;
+      if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+    }
+    if (lane == 0) { bv[warp] = best; bi[warp] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float b = bv[0]; int id = bi[0];
+      for (int w = 1; w < (blockDim.x >> 5); ++w)
+        if (bv[w] > b || (bv[w] == b && bi[w] < id)) { b = bv[w]; id = bi[w]; }
+      chosen[round] = id;
+      ids[(long long)blockIdx.x * k + round] = id;
+      vals[(long long)blockIdx.x * k + round] = b;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- CTC prefix scorer
+// Initial state (ctc_prefix_score.py:86-95): r[t][0] = logzero, r[t][1] = cumsum_t x[t][blank]; s_prev = 0.
+__global__ void ctc_init_state_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank, int W, int n,
+                                      float* __restrict__ r, float* __restrict__ s_prev) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int u = s / W;
+  const int T = lens[u];
+  float* rr = r + (long long)s * Tmax * 2;
+  float c = 0.f;
+  for (int t = 0; t < Tmax; ++t) {
+    if (t < T) c += logp[((long long)u * Tmax + t) * V + blank];
+    rr[2 * t] = LOGZERO;
+    rr[2 * t + 1] = (t < T) ? c : LOGZERO;
+  }
+  s_prev[s] = 0.f;
+}
+
+struct CtcRec {  // one forward recursion for prefix g of slot s extended by token c
+  float log_psi;
+};
+
+// Runs the recursion of ctc_prefix_score.py:128-182 for one (slot, token). If r_out != null the new
+// forward variables r_out[t][0..1] are stored (state of the extended prefix).
+__device__ __forceinline__ float ctc_prefix_recursion(const float* __restrict__ x /* logp of utt: [T][V] */, int V, int T, int blank, int eos,
+                                                      const float* __restrict__ rp /* [T][2] */, int c, int last, int out_len,
+                                                      float* __restrict__ r_out, int Tmax) {
+  if (c == eos) {  // (:184-185) log_psi[eos] = r_sum[T-1]
+    if (r_out) for (int t = 0; t < Tmax; ++t) { r_out[2 * t] = LOGZERO; r_out[2 * t + 1] = LOGZERO; }
+    return logaddexp(rp[2 * (T - 1)], rp[2 * (T - 1) + 1]);
+  }
+  const int start = max(out_len, 1);
+  float rn = LOGZERO, rb = LOGZERO;
+  if (out_len == 0) rn = x[c];  // r[0,0] = x[0,c]
+  if (r_out) {
+    for (int t = 0; t < start - 1; ++t) { r_out[2 * t] = LOGZERO; r_out[2 * t + 1] = LOGZERO; }
+    r_out[2 * (start - 1)] = rn; r_out[2 * (start - 1) + 1] = rb;
+  }
+  // log_psi = logsumexp( {log_phi[t-1] + x[t,c]}_{t=start..T-1}, r[start-1,0] ): streaming max/sum
+  float m = rn, ssum = 1.f;  // first element r[start-1,0]
+  const bool same = (c == last);
+  for (int t = start; t < T; ++t) {
+    const float p0 = rp[2 * (t - 1)], p1 = rp[2 * (t - 1) + 1];
+    const float phi = same ? p1 : logaddexp(p0, p1);
+    const float xc = x[(long long)t * V + c], xb = x[(long long)t * V + blank];
+    const float nrn = logaddexp(rn, phi) + xc;
+    const float nrb = logaddexp(rn, rb) + xb;
+    rn = nrn; rb = nrb;
+    if (r_out) { r_out[2 * t] = rn; r_out[2 * t + 1] = rb; }
+    const float e = phi + xc;
+    if (e > m) { ssum = ssum * expf(m - e) + 1.f; m = e; } else { ssum += expf(e - m); }
+  }
+  if (r_out) for (int t = T; t < Tmax; ++t) { r_out[2 * t] = LOGZERO; r_out[2 * t + 1] = LOGZERO; }
+  float psi = m + logf(ssum);
+  if (c == blank) psi = LOGZERO;  // (:187-189)
+  return psi;
+}
+
+// Scores for candidate lists: cand [n][P] (from the pre-beam) plus eos as candidate P. Outputs part[n][P+1] = log_psi - s_prev
+// and psi[n][P+1]. Duplicate eos (eos already among the P) is flagged by valid[n][P+1] = 0.
+__global__ void __launch_bounds__(128) ctc_score_cands_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank,
+                                                              int eos, int W, int n, const float* __restrict__ r_prev, const float* __restrict__ s_prev,
+                                                              const int* __restrict__ last_tok, int out_len, const int* __restrict__ cand, int P,
+                                                              float* __restrict__ part, float* __restrict__ psi, int* __restrict__ valid) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * (P + 1)) return;
+  const int s = idx / (P + 1), j = idx % (P + 1);
+  const int u = s / W;
+  int c = (j < P) ? cand[(long long)s * P + j] : eos;
+  int ok = 1;
+  if (j == P) for (int q = 0; q < P; ++q) if (cand[(long long)s * P + q] == eos) ok = 0;
+  const float v = ctc_prefix_recursion(logp + (long long)u * Tmax * V, V, lens[u], blank, eos, r_prev + (long long)s * Tmax * 2, c, last_tok[s],
+                                       out_len, nullptr, Tmax);
+  psi[idx] = v;
+  part[idx] = v - s_prev[s];
+  valid[idx] = ok;
+}
+
+// Dense variant (ctc_weight == 1: no pre-beam, ctc_prefix_score.py:118-122): part[n][V].
+__global__ void __launch_bounds__(128) ctc_score_dense_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank,
+                                                              int eos, int W, int n, const float* __restrict__ r_prev, const float* __restrict__ s_prev,
+                                                              const int* __restrict__ last_tok, int out_len, float* __restrict__ part) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * V) return;
+  const int s = (int)(idx / V), c = (int)(idx % V);
+  const int u = s / W;
+  const float v = ctc_prefix_recursion(logp + (long long)u * Tmax * V, V, lens[u], blank, eos, r_prev + (long long)s * Tmax * 2, c, last_tok[s],
+                                       out_len, nullptr, Tmax);
+  part[idx] = v - s_prev[s];
+}
+
+// ---------------------------------------------------------------- beam selection + post-process, one warp per utterance
+struct BeamState {
+  // per slot (n = U*W), "cur" read / "nxt" written
+  const float* score; const float* sc_dec; const float* sc_ctc; const int* active;
+  float* n_score; float* n_sc_dec; float* n_sc_ctc; int* n_active; int* n_last_tok;
+  int* n_parent;      // [n] parent slot of each new slot (ancestor-table / CTC-state gathers)
+  int* bp_parent; int* bp_token;   // [maxlen][n] back-pointers for sequence reconstruction
+  // ended hypotheses: per utterance append (step, slot, score, dec, ctc)
+  int* ended_count; int* ended_step; int* ended_slot; float* ended_score; float* ended_dec; float* ended_ctc; int ended_cap;
+  float* best_at_step;  // [U][maxlen_cap] best ended score per step (end detection)
+  float* best_all;      // [U]
+  int* utt_done;        // [U]
+};
+
+// mode 0: decoder only      -- cand_val[n][P] = w_dec*logp of cand_ids; total = (val + penalty) + score
+// mode 1: joint             -- candidates j<P from the pre-beam + eos as candidate P; part/valid [n][P+1]
+//                              total = ((dec + penalty) + w_ctc*part) + score   (batch_beam_search.py:293-309)
+// mode 2: CTC only (dense)  -- cand_val[n][P] = w_ctc*part of cand_ids, part = dense [n][V]
+__global__ void __launch_bounds__(32) beam_select_kernel(BeamState st, int U, int W, int P, int V, int step, const int* __restrict__ maxlen,
+                                                         const int* __restrict__ minlen, int eos, float w_dec, float w_ctc, float penalty, int mode,
+                                                         const int* __restrict__ cand_ids, const float* __restrict__ cand_val,
+                                                         const float* __restrict__ logp_dec /* [n][V] or null */, const float* __restrict__ part,
+                                                         const int* __restrict__ valid, int end_detect, int maxlen_cap) {
+  const int u = blockIdx.x, lane = threadIdx.x;
+  const int PC = (mode == 1) ? P + 1 : P;   // candidates per slot
+  const int total = W * PC;
+  constexpr int MAXC = 24;                  // each lane owns candidates lane, lane+32, ...: supports W*PC <= 768
+  float tot[MAXC];
+  const bool done = st.utt_done[u] != 0;
+#pragma unroll
+  for (int q = 0; q < MAXC; ++q) {
+    const int ci = lane + q * 32;
+    float t = -INFINITY;
+    if (ci < total && !done) {
+      const int w = ci / PC, j = ci % PC, s = u * W + w;
+      if (st.active[s]) {
+        if (mode == 1) {
+          if (valid[(long long)s * PC + j]) {
+            const float dec = (j < P) ? cand_val[(long long)s * P + j] : w_dec * logp_dec[(long long)s * V + eos];
+            t = ((dec + penalty) + w_ctc * part[(long long)s * PC + j]) + st.score[s];
+          }
+        } else {
+          t = (cand_val[(long long)s * P + j] + penalty) + st.score[s];
+        }
+      }
+    }
+    tot[q] = t;
+  }
+  const int mlen = maxlen[u];
+  const bool last_step = (step == mlen - 1);
+  float step_best = -INFINITY;
+  for (int k = 0; k < W; ++k) {
+    // warp arg-max over the remaining candidates (ties -> lower flat index)
+    float best = -INFINITY; int bidx = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) {
+      const int ci = lane + q * 32;
+      if (tot[q] > best) { best = tot[q]; bidx = ci; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    const int ns = u * W + k;
+    const long long bp = (long long)step * U * W + ns;
+    if (best == -INFINITY) {                // fewer candidates than beam slots (utterance finished)
+      if (lane == 0) {
+        st.n_active[ns] = 0; st.n_score[ns] = 0.f; st.n_sc_dec[ns] = 0.f; st.n_sc_ctc[ns] = 0.f; st.n_last_tok[ns] = eos;
+        st.n_parent[ns] = ns; st.bp_parent[bp] = -1; st.bp_token[bp] = eos;
+      }
+      continue;
+    }
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) if (lane + q * 32 == bidx) tot[q] = -INFINITY;   // remove the winner
+    if (lane == 0) {
+      const int w = bidx / PC, j = bidx % PC, s = u * W + w;
+      const int tok = (mode == 1 && j == P) ? eos : cand_ids[(long long)s * P + j];
+      float dlogp = 0.f, cpart = 0.f;
+      if (mode != 2) dlogp = logp_dec[(long long)s * V + tok];
+      if (mode == 1) cpart = part[(long long)s * PC + j];
+      if (mode == 2) cpart = part[(long long)s * V + tok];
+      const float ndec = st.sc_dec[s] + dlogp, nctc = st.sc_ctc[s] + cpart;
+      st.bp_parent[bp] = s; st.bp_token[bp] = tok;
+      st.n_parent[ns] = s;
+      st.n_score[ns] = best; st.n_sc_dec[ns] = ndec; st.n_sc_ctc[ns] = nctc; st.n_last_tok[ns] = tok;
+      const bool ended = last_step || tok == eos;   // last step: eos is appended to every hypothesis (batch_beam_search.py:392-407)
+      st.n_active[ns] = ended ? 0 : 1;
+      if (ended && step >= minlen[u]) {
+        const int e = st.ended_count[u];
+        if (e < st.ended_cap) {
+          const long long o = (long long)u * st.ended_cap + e;
+          st.ended_step[o] = step; st.ended_slot[o] = ns; st.ended_score[o] = best; st.ended_dec[o] = ndec; st.ended_ctc[o] = nctc;
+          st.ended_count[u] = e + 1;
+        }
+        step_best = fmaxf(step_best, best);
+      }
+    }
+  }
+  if (lane == 0 && !done) {
+    if (end_detect) {
+      // end_detect(ended, i) (e2e_asr_common.py:14-44): hypotheses with len(yseq) == i-m ended at step i-m-2
+      if (step < maxlen_cap) st.best_at_step[(long long)u * maxlen_cap + step] = step_best;
+      const float ball = fmaxf(st.best_all[u], step_best);
+      st.best_all[u] = ball;
+      int count = 0;
+      for (int m = 0; m < 3; ++m) {
+        const int j = step - m - 2;
+        if (j >= 0 && j < maxlen_cap) {
+          const float bs = st.best_at_step[(long long)u * maxlen_cap + j];
+          if (bs > -INFINITY && bs - ball < -10.0f) ++count;
+        }
+      }
+      if (count == 3) st.utt_done[u] = 1;
+    }
+    if (last_step) st.utt_done[u] = 1;
+  }
+}
+
+// After selection: rows of the ancestor table and CTC states follow their parents.
+__global__ void anc_update_kernel(const int* __restrict__ anc, int* __restrict__ n_anc, int anc_ld, const int* __restrict__ parent, int pos, int n) {
+  const int s = blockIdx.x;
+  const int p = parent[s];
+  for (int j = threadIdx.x; j < pos; j += blockDim.x) n_anc[(long long)s * anc_ld + j] = anc[(long long)p * anc_ld + j];
+  if (threadIdx.x == 0) n_anc[(long long)s * anc_ld + pos] = p;
+}
+
+// New CTC forward variables of each surviving slot: recursion for (parent state, chosen token), storing r.
+__global__ void __launch_bounds__(32) ctc_advance_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank, int eos,
+                                                         int W, int n, const float* __restrict__ r_prev, const int* __restrict__ parent,
+                                                         const int* __restrict__ par_last_tok, const int* __restrict__ new_tok,
+                                                         const int* __restrict__ new_active, int out_len, float* __restrict__ r_new,
+                                                         float* __restrict__ s_new) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int u = s / W;
+  float* ro = r_new + (long long)s * Tmax * 2;
+  if (!new_active[s]) {
+    for (int t = 0; t < Tmax; ++t) { ro[2 * t] = LOGZERO; ro[2 * t + 1] = LOGZERO; }
+    s_new[s] = 0.f;
+    return;
+  }
+  const int p = parent[s];
+  const float psi = ctc_prefix_recursion(logp + (long long)u * Tmax * V, V, lens[u], blank, eos, r_prev + (long long)p * Tmax * 2, new_tok[s],
+                                         par_last_tok[p], out_len, ro, Tmax);
+  s_new[s] = psi;
+}
+
+__global__ void count_active_kernel(const int* __restrict__ active, int n, int* __restrict__ out) {
+  __shared__ float red[33];
+  float c = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += active[i] ? 1.f : 0.f;
+  c = espb::block_sum(c, red);
+  if (threadIdx.x == 0) out[0] = (int)c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int espb_dec_embed_f32(const int* last_tok, const float* emb, const float* pe, int pos, int n, int D, float scale, float* x, cudaStream_t stream) {
+  dec_embed_kernel<<<n, 128, 0, stream>>>(last_tok, emb, pe, pos, D, scale, x);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_dec_self_attn_f32(const float* qkv, float* kc, float* vc, const int* anc, int anc_ld, int n, int D, int H, int pos, float* ctx,
+                           long long ctx_plane, cudaStream_t stream) {
+  const int warps = 4;
+  const size_t smem = (size_t)warps * (pos + 1) * sizeof(float);
+  if (smem > 48 * 1024) { espb_set_error("dec_self_attn: prefix too long for the score buffer"); return ESPB_ERR_ARG; }
+  dec_self_attn_kernel<<<(n * H + warps - 1) / warps, warps * 32, smem, stream>>>(qkv, kc, vc, anc, anc_ld, n, D, H, pos, ctx, ctx_plane);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_dec_src_attn_f32(const float* q, const float* kv, long long kv_ld, int k_off, int v_off, int U, int Tmax, const int* lens, int W, int D,
+                          int H, float* ctx, long long ctx_plane, cudaStream_t stream) {
+  const int dk = D / H;
+  if (W > 16 || dk > 256 || (dk & 3) || 256 % dk) { espb_set_error("dec_src_attn: needs beam <= 16 and d_k in {4..256} dividing 256"); return ESPB_ERR_ARG; }
+  const int ngrp = 256 / dk;
+  const size_t smem = ((size_t)W * dk + (size_t)W * Tmax + (size_t)ngrp * W * dk) * sizeof(float);
+  if (smem > 200 * 1024) { espb_set_error("dec_src_attn: beam*T too large for shared memory"); return ESPB_ERR_ARG; }
+  static size_t cur_max = 48 * 1024;
+  if (smem > cur_max) {
+    if (cudaFuncSetAttribute(dec_src_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
+      espb_set_error("dec_src_attn: cannot raise dynamic shared memory"); return ESPB_ERR_CUDA;
+    }
+    cur_max = 200 * 1024;
+  }
+  dec_src_attn_kernel<<<U * H, 256, smem, stream>>>(q, kv, kv_ld, k_off, v_off, Tmax, lens, W, D, H, ctx, ctx_plane);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_rows_topk_f32(const float* x, long long rows, long long ld, int V, float scale, int k, int* ids, float* vals, cudaStream_t stream) {
+  if (k > 64 || k > V) { espb_set_error("rows_topk: k must be <= min(64, V)"); return ESPB_ERR_ARG; }
+  rows_topk_kernel<<<(unsigned)rows, 256, 0, stream>>>(x, ld, V, scale, k, ids, vals);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_ctc_init_state_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int W, float* r, float* s_prev,
+                            cudaStream_t stream) {
+  const int n = U * W;
+  ctc_init_state_kernel<<<(n + 63) / 64, 64, 0, stream>>>(logp, Tmax, V, lens, blank, W, n, r, s_prev);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_ctc_score_cands_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
+                             const float* s_prev, const int* last_tok, int out_len, const int* cand, int P, float* part, float* psi, int* valid,
+                             cudaStream_t stream) {
+  const int n = U * W, tot = n * (P + 1);
+  ctc_score_cands_kernel<<<(tot + 127) / 128, 128, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, s_prev, last_tok, out_len, cand, P,
+                                                                part, psi, valid);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_ctc_score_dense_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
+                             const float* s_prev, const int* last_tok, int out_len, float* part, cudaStream_t stream) {
+  const long long tot = (long long)U * W * V;
+  ctc_score_dense_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, U * W, r_prev, s_prev, last_tok,
+                                                                           out_len, part);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_beam_select(const float* score, const float* sc_dec, const float* sc_ctc, const int* active, float* n_score, float* n_sc_dec,
+                     float* n_sc_ctc, int* n_active, int* n_last_tok, int* n_parent, int* bp_parent, int* bp_token, int* ended_count,
+                     int* ended_step, int* ended_slot, float* ended_score, float* ended_dec, float* ended_ctc, int ended_cap, float* best_at_step,
+                     float* best_all, int* utt_done, int U, int W, int P, int V, int step, const int* maxlen, const int* minlen, int eos,
+                     float w_dec, float w_ctc, float penalty, int mode, const int* cand_ids, const float* cand_val, const float* logp_dec,
+                     const float* part, const int* valid, int end_detect, int maxlen_cap, cudaStream_t stream) {
+  const int PC = (mode == 1) ? P + 1 : P;
+  if (W * PC > 768 || W > 32 || mode < 0 || mode > 2) { espb_set_error("beam_select: beam * candidates > 768 or bad mode"); return ESPB_ERR_ARG; }
+  BeamState st{score, sc_dec, sc_ctc, active, n_score, n_sc_dec, n_sc_ctc, n_active, n_last_tok, n_parent, bp_parent, bp_token,
+               ended_count, ended_step, ended_slot, ended_score, ended_dec, ended_ctc, ended_cap, best_at_step, best_all, utt_done};
+  beam_select_kernel<<<U, 32, 0, stream>>>(st, U, W, P, V, step, maxlen, minlen, eos, w_dec, w_ctc, penalty, mode, cand_ids, cand_val, logp_dec,
+                                           part, valid, end_detect, maxlen_cap);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_anc_update_i32(const int* anc, int* n_anc, int anc_ld, const int* parent, int pos, int n, cudaStream_t stream) {
+  anc_update_kernel<<<n, 64, 0, stream>>>(anc, n_anc, anc_ld, parent, pos, n);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_ctc_advance_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
+                         const int* parent, const int* par_last_tok, const int* new_tok, const int* new_active, int out_len, float* r_new,
+                         float* s_new, cudaStream_t stream) {
+  const int n = U * W;
+  ctc_advance_kernel<<<(n + 31) / 32, 32, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, parent, par_last_tok, new_tok, new_active,
+                                                       out_len, r_new, s_new);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_count_active_i32(const int* active, int n, int* out, cudaStream_t stream) {
+  count_active_kernel<<<1, 256, 0, stream>>>(active, n, out);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+}  // extern "C"

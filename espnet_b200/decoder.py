@@ -1,0 +1,171 @@
+"""TransformerDecoder with the reference's constructor / state_dict surface, as an incremental device-side
+scorer: cross-attention K/V are projected once per utterance (shared by the whole beam) and the
+self-attention K/V of each new token are appended to a position-major cache addressed through an
+ancestor table, instead of re-projecting the prefix and the memory every step as the reference does.
+
+Reference: espnet2/asr/decoder/transformer_decoder.py:60-311, 413-470;
+espnet2/legacy/nets/pytorch_backend/transformer/decoder_layer.py:73-179 (cache branch), attention.py:153-265
+(default branch, no flash/sdpa), embedding.py:38-95 (PositionalEncoding).
+"""
+import math
+from typing import List
+
+import torch
+
+from . import ops
+from .lib import call, ptr
+from .ops import ACT_RELU, _count, layernorm, linear, new_split, split_from
+
+LN_EPS = 1e-12
+
+
+class _MHA(torch.nn.Module):
+    def __init__(self, n_feat):
+        super().__init__()
+        self.linear_q = torch.nn.Linear(n_feat, n_feat)
+        self.linear_k = torch.nn.Linear(n_feat, n_feat)
+        self.linear_v = torch.nn.Linear(n_feat, n_feat)
+        self.linear_out = torch.nn.Linear(n_feat, n_feat)
+
+
+class _FFN(torch.nn.Module):
+    def __init__(self, d, units):
+        super().__init__()
+        self.w_1 = torch.nn.Linear(d, units)
+        self.w_2 = torch.nn.Linear(units, d)
+
+
+class _DecoderLayer(torch.nn.Module):
+    def __init__(self, d, units):
+        super().__init__()
+        self.self_attn, self.src_attn = _MHA(d), _MHA(d)
+        self.feed_forward = _FFN(d, units)
+        self.norm1 = torch.nn.LayerNorm(d, eps=LN_EPS)
+        self.norm2 = torch.nn.LayerNorm(d, eps=LN_EPS)
+        self.norm3 = torch.nn.LayerNorm(d, eps=LN_EPS)
+
+
+def pos_enc_table(length, d):
+    """PositionalEncoding.extend_pe (embedding.py:62-83)."""
+    pos = torch.arange(0, length, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * -(math.log(10000.0) / d))
+    pe = torch.zeros(length, d)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+class TransformerDecoder(torch.nn.Module):
+    """Drop-in container for espnet2.asr.decoder.transformer_decoder.TransformerDecoder (inference scorer)."""
+
+    def __init__(self, vocab_size: int, encoder_output_size: int, attention_heads: int = 4, linear_units: int = 2048,
+                 num_blocks: int = 6, dropout_rate: float = 0.1, positional_dropout_rate: float = 0.1,
+                 self_attention_dropout_rate: float = 0.0, src_attention_dropout_rate: float = 0.0, input_layer: str = "embed",
+                 use_output_layer: bool = True, pos_enc_class=None, normalize_before: bool = True, concat_after: bool = False,
+                 layer_drop_rate: float = 0.0, qk_norm: bool = False, use_flash_attn: bool = True,
+                 gradient_checkpoint_layers: List[int] = []):
+        super().__init__()
+        if input_layer != "embed" or not use_output_layer or not normalize_before or concat_after or qk_norm:
+            raise NotImplementedError("espnet_b200 TransformerDecoder: embed input, output layer, pre-LN, no concat_after/qk_norm")
+        d = encoder_output_size
+        self.d, self.heads, self.units, self.num_blocks, self.odim = d, attention_heads, linear_units, num_blocks, vocab_size
+        self.embed = torch.nn.Sequential(torch.nn.Embedding(vocab_size, d))
+        self.decoders = torch.nn.ModuleList(_DecoderLayer(d, linear_units) for _ in range(num_blocks))
+        self.after_norm = torch.nn.LayerNorm(d, eps=LN_EPS)
+        self.output_layer = torch.nn.Linear(d, vocab_size)
+        self._packed = None
+        self._ws = {}
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._packed = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _pack(self):
+        dev = self.after_norm.weight.device
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()  # noqa: E731
+        pk = dict(emb=f32(self.embed[0].weight), layers=[])
+        kvw, kvb = [], []
+        for lyr in self.decoders:
+            sa, ca, ff = lyr.self_attn, lyr.src_attn, lyr.feed_forward
+            d = dict(
+                n1=(f32(lyr.norm1.weight), f32(lyr.norm1.bias)), n2=(f32(lyr.norm2.weight), f32(lyr.norm2.bias)),
+                n3=(f32(lyr.norm3.weight), f32(lyr.norm3.bias)),
+                qkv_w=split_from(torch.cat([f32(sa.linear_q.weight), f32(sa.linear_k.weight), f32(sa.linear_v.weight)], 0)),
+                qkv_b=torch.cat([f32(sa.linear_q.bias), f32(sa.linear_k.bias), f32(sa.linear_v.bias)], 0),
+                so_w=split_from(f32(sa.linear_out.weight)), so_b=f32(sa.linear_out.bias),
+                cq_w=split_from(f32(ca.linear_q.weight)), cq_b=f32(ca.linear_q.bias),
+                co_w=split_from(f32(ca.linear_out.weight)), co_b=f32(ca.linear_out.bias),
+                w1=split_from(f32(ff.w_1.weight)), b1=f32(ff.w_1.bias), w2=split_from(f32(ff.w_2.weight)), b2=f32(ff.w_2.bias))
+            kvw += [f32(ca.linear_k.weight), f32(ca.linear_v.weight)]
+            kvb += [f32(ca.linear_k.bias), f32(ca.linear_v.bias)]
+            pk["layers"].append(d)
+        pk["kv_w"], pk["kv_b"] = split_from(torch.cat(kvw, 0)), torch.cat(kvb, 0)  # [L*2D][D]: per layer k rows then v rows
+        pk["an"] = (f32(self.after_norm.weight), f32(self.after_norm.bias))
+        pk["out_w"], pk["out_b"] = split_from(f32(self.output_layer.weight)), f32(self.output_layer.bias)
+        self._packed = pk
+        return pk
+
+    def _buf(self, name, shape, dtype=torch.float32, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            for k in [k for k in self._ws if k[0] == name]:
+                del self._ws[k]
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.after_norm.weight.device)
+            self._ws[key] = t
+        return t
+
+    # ---------------------------------------------------------------- device-side incremental scorer
+    @torch.no_grad()
+    def init_memory(self, enc_split, U, Tmax, lens32, n_slots, max_len):
+        """Project the encoder memory once: kv [U*Tmax][L*2D] (k_l | v_l per layer); allocate the self-attention cache."""
+        pk = self._packed or self._pack()
+        L, D = self.num_blocks, self.d
+        kv = self._buf("kv", (U * Tmax, L * 2 * D))
+        linear(enc_split, pk["kv_w"], kv, bias=pk["kv_b"])
+        st = dict(kv=kv, U=U, Tmax=Tmax, lens32=lens32, n=n_slots, max_len=max_len,
+                  kc=self._buf("kc", (L, max_len, n_slots, D)), vc=self._buf("vc", (L, max_len, n_slots, D)),
+                  pe=self._pe(max_len))
+        return st
+
+    def _pe(self, length):
+        key = ("pe", length)
+        if key not in self._ws:
+            self._ws[key] = pos_enc_table(length, self.d).to(self.after_norm.weight.device)
+        return self._ws[key]
+
+    @torch.no_grad()
+    def step(self, st, pos, last_tok, anc, W):
+        """One decoding position for all n slots: returns log-probabilities [n][V] (buffer reused across steps).
+        Equivalent of batch_score/forward_one_step (transformer_decoder.py:262-311,191-238)."""
+        pk = self._packed
+        n, D, H, L, Uu = st["n"], self.d, self.heads, self.num_blocks, self.units
+        x = self._buf("x", (n, D))
+        xn = self._buf("xn", (2, n, D))
+        qkv = self._buf("qkv", (n, 3 * D))
+        ctx = self._buf("ctx", (2, n, D))
+        q = self._buf("q", (n, D))
+        h = self._buf("h", (2, n, Uu))
+        call("espb_dec_embed_f32", ptr(last_tok), ptr(pk["emb"]), ptr(st["pe"]), pos, n, D, math.sqrt(D), ptr(x))
+        _count()
+        for li, w in enumerate(pk["layers"]):
+            layernorm(x, *w["n1"], LN_EPS, out_split=xn)
+            linear(xn, w["qkv_w"], qkv, bias=w["qkv_b"])
+            call("espb_dec_self_attn_f32", ptr(qkv), ptr(st["kc"][li]), ptr(st["vc"][li]), ptr(anc), anc.shape[1], n, D, H, pos,
+                 ptr(ctx), n * D)
+            _count()
+            linear(ctx, w["so_w"], x, bias=w["so_b"], residual=x)
+            layernorm(x, *w["n2"], LN_EPS, out_split=xn)
+            linear(xn, w["cq_w"], q, bias=w["cq_b"])
+            call("espb_dec_src_attn_f32", ptr(q), ptr(st["kv"]), L * 2 * D, li * 2 * D, li * 2 * D + D, st["U"], st["Tmax"],
+                 ptr(st["lens32"]), W, D, H, ptr(ctx), n * D)
+            _count()
+            linear(ctx, w["co_w"], x, bias=w["co_b"], residual=x)
+            layernorm(x, *w["n3"], LN_EPS, out_split=xn)
+            linear(xn, w["w1"], h, bias=w["b1"], act=ACT_RELU, split_out=True)
+            linear(h, w["w2"], x, bias=w["b2"], residual=x)
+        layernorm(x, *pk["an"], LN_EPS, out_split=xn)
+        logp = self._buf("logp", (n, self.odim))
+        linear(xn, pk["out_w"], logp, bias=pk["out_b"])
+        ops.log_softmax_rows_(logp)
+        return logp
