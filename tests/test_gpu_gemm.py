@@ -2,7 +2,10 @@
 import pytest
 import torch
 
+import os
+
 pytestmark = pytest.mark.gpu
+MODES = [m for m in os.environ.get("ESPB_TEST_GEMM_MODES", "simt,tc").split(",") if m]
 
 
 def _split(x):
@@ -29,7 +32,7 @@ SHAPES = [(128, 64, 32), (128, 256, 64), (200, 130, 96), (640, 512, 512), (937, 
           (1000, 1536, 512), (129, 65, 33 * 4)]
 
 
-@pytest.mark.parametrize("mode", ["simt", "tc"])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_linear_plain(mode, M, N, K):
     from espnet_b200 import ops
@@ -46,7 +49,7 @@ def test_linear_plain(mode, M, N, K):
     assert err < 2e-5, f"{mode} M{M} N{N} K{K} max abs err {err}"
 
 
-@pytest.mark.parametrize("mode", ["simt", "tc"])
+@pytest.mark.parametrize("mode", MODES)
 def test_linear_epilogues(mode):
     from espnet_b200 import ops
 
@@ -70,7 +73,7 @@ def test_linear_epilogues(mode):
     assert (x.double() - _ref(a, b, bias, res=res, alpha=0.5)).abs().max().item() < 2e-5
 
 
-@pytest.mark.parametrize("mode", ["simt", "tc"])
+@pytest.mark.parametrize("mode", MODES)
 def test_batched_strided_attention_shapes(mode):
     """The three attention GEMMs' addressing: heads as batch-x, utterances as batch-y, shared B operand, K tail."""
     from espnet_b200 import ops
@@ -109,7 +112,7 @@ def test_batched_strided_attention_shapes(mode):
     assert ((ctx[0].double() + ctx[1].double()) - ref).abs().max().item() < 2e-5
 
 
-@pytest.mark.parametrize("mode", ["simt", "tc"])
+@pytest.mark.parametrize("mode", MODES)
 def test_conv2_implicit_gemm_and_outer_k(mode):
     """conv1 kernel -> conv2 as implicit GEMM over the parity-split layout -> embed.out with the K axis split over f."""
     import math
