@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- utterances/sec of the Speech2Text hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # espnet_b200 CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port) on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic 16 kHz waveforms: BASELINE.json configs[1],
+Conformer-large (12L/512d/8h, ff 2048, conv2d, macaron, rel-pos latest, kernel 31) + 6L Transformer decoder,
+V=5000, joint CTC/attention decoding (ctc_weight 0.3, beam 10, maxlenratio -64), batch 64 x 30 s per GPU.
+`value` times encode+search with the waveforms resident in HBM; `e2e` times Speech2Text.batch_decode_padded from
+pinned host memory to host-side hypotheses (H2D + D2H inside the timed region).  Multi-GPU: utterances are
+sharded (weak scaling, one batch per rank, no data-path collective) and the final hypotheses are all-gathered.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (model cfg, seconds, batch per GPU, beam, ctc_weight, maxlenratio)
+    "conformer_large_joint_64x30s": (dict(d_model=512, heads=8, ff=2048, enc_layers=12, dec_layers=6, vocab=5000, kernel=31), 30, 64, 10, 0.3, -64.0),
+    "conformer_large_joint_32x15s": (dict(d_model=512, heads=8, ff=2048, enc_layers=12, dec_layers=6, vocab=5000, kernel=31), 15, 32, 10, 0.3, -64.0),
+    "conformer_4l256_joint_8x5s": (dict(d_model=256, heads=4, ff=2048, enc_layers=4, dec_layers=2, vocab=5000, kernel=31), 5, 8, 10, 0.3, -16.0),
+}
+METRIC = "utterances/sec (RTF) Conformer-large ASR inference at 1/2/4/8 B200 vs CPU ref"
+
+
+def waveforms(n, nsamples, offset=0):
+    out = torch.empty(n, nsamples)
+    for i in range(n):
+        g = torch.Generator().manual_seed(1234 + offset + i)
+        out[i] = 0.1 * torch.randn(nsamples, generator=g)
+    return out
+
+
+def model_weights(cfg):
+    from gpu_util import random_weights
+
+    return random_weights(cfg, seed=0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, bf16 sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args, rank, world):
+    """Reference CPU path = the oracle port (pure torch CPU restatement; the reference itself is Python and cannot
+    travel to the GPU box).  One step = one utterance of the workload decoded batch-1, as Speech2Text does."""
+    if rank != 0:
+        return
+    import oracle
+
+    cfg, secs, batch, beam, ctcw, mlr = WORKLOADS[args.workload]
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = model_weights(cfg)
+    o = oracle.OracleSpeech2Text(cfg, w, beam_size=beam, ctc_weight=ctcw, maxlenratio=mlr, nbest=1)
+    waves = waveforms(args.warmup + args.steps, secs * 16000)
+    for i in range(args.warmup):
+        o(waves[i])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        o(waves[args.warmup + i])
+    dt = time.perf_counter() - t0
+    ups = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ups, "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "rtf": (dt / args.steps) / secs,
+        "config": {"workload": args.workload, "sample": "1 utterance per step, batch-1 (as the reference decodes)", "beam": beam,
+                   "ctc_weight": ctcw, "maxlenratio": mlr, "utt_seconds": secs},
+        "cpu_baseline": {"value": ups, "unit": "utterances/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} x 1 utterance of {secs} s, batch-1, {args.warmup} warm-up"},
+        "e2e": {"value": ups, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- espnet_b200 arm
+def run_b200(args, rank, local_rank, world):
+    import torch.distributed as dist
+
+    import espnet_b200
+    from espnet_b200 import ops
+    from gpu_util import speech2text
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg, secs, batch, beam, ctcw, mlr = WORKLOADS[args.workload]
+    nsamp = secs * 16000
+    s2t = speech2text(cfg, model_weights(cfg), beam_size=beam, ctc_weight=ctcw, maxlenratio=mlr, nbest=1)
+    host = waveforms(batch, nsamp, offset=rank * batch).pin_memory()      # utterances sharded by rank
+    lens = torch.full((batch,), nsamp, dtype=torch.long)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(speech_dev):
+        enc, enc_lens = s2t.asr_model.encode(speech_dev, lens)
+        return s2t.beam_search.forward_batch(enc, enc_lens, s2t.asr_model.enc_split(enc), mlr, 0.0)
+
+    def step_e2e():
+        res = s2t.batch_decode_padded(host, lens)
+        if world > 1:   # single exchange of the path: all-gather of fixed-width hypothesis records
+            rec = torch.full((batch, 80), -1, dtype=torch.int32, device=dev)
+            for i, r in enumerate(res):
+                ids = r[0][2][:78] if r else []
+                rec[i, 0] = len(ids)
+                if ids:
+                    rec[i, 1:1 + len(ids)] = torch.tensor(ids, dtype=torch.int32)
+            out = torch.empty(world * batch, 80, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(out, rec)
+            out.cpu()
+        return res
+
+    speech_dev = host.to(dev)
+    for _ in range(args.warmup):
+        step_resident(speech_dev)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+
+    # ---- timed: K resident steps (per-step CUDA events, L2 flushed between steps, not timed)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ops.launch_counter[0] = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        res = step_resident(speech_dev)
+        b.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ops.launch_counter[0]
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    # ---- timed: K end-to-end steps
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev2:
+        flush.zero_()
+        a.record()
+        res = step_e2e()
+        b.record()
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    clocks = sampler.stop()
+    n_hyp_tokens = sum(len(r[0][2]) for r in res if r)
+
+    # ---- roofline of the dominant kernel (tcgen05 3xTF32 GEMM): per-launch CUDA events over one extra step
+    ops.gemm_profile = []
+    step_resident(speech_dev)
+    torch.cuda.synchronize()
+    prof = ops.gemm_profile
+    ops.gemm_profile = None
+    g_flops = sum(p[0] for p in prof)
+    g_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
+    peak_tf, hbm_gbs, peak_src = measured_peaks()
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    if rank != 0:
+        return
+    utts = world * batch * args.steps
+    value = utts / (dev_ms / 1000.0)
+    e2e = utts / (e2e_ms / 1000.0)
+    ach = g_flops / (g_ms / 1000.0) / 1e12 if g_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "rtf": (dev_ms / 1000.0) / (utts * secs),
+        "config": {"workload": args.workload, "global_batch": world * batch, "utt_seconds": secs, "beam": beam, "ctc_weight": ctcw,
+                   "maxlenratio": mlr, "vocab": cfg["vocab"], "parallelism": f"utterance-sharded x{world}", "l2": "flushed between steps (256 MiB write)",
+                   "gemm": "tcgen05 kind::tf32 x3 (error-compensated fp32)", "wall_s_timed_region": wall},
+        "e2e": {"value": e2e, "unit": "utterances/s", "h2d_bytes_per_step": batch * nsamp * 4,
+                "d2h_bytes_per_step": int(2 * 4 * 64 * batch * beam + 6 * 4 * batch * beam * 64), "ms_per_step": e2e_ms / args.steps,
+                "hyp_tokens_last_step": n_hyp_tokens},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tf32x3_kernel (all launches of one step)", "achieved": ach, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
+                     "launches": len(prof), "gemm_ms_per_step": g_ms,
+                     "note": "algorithmic FLOPs (2MNK); each is executed as 3 tf32 MMAs at half the bf16 rate, so 1/6 of the bf16 peak is the ceiling of this formulation"},
+    }
+    if args.cpu_baseline and world >= 1:
+        import oracle
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        o = oracle.OracleSpeech2Text(cfg, model_weights(cfg), beam_size=beam, ctc_weight=ctcw, maxlenratio=mlr, nbest=1)
+        t0 = time.perf_counter()
+        ref = o(host[0])
+        dt = time.perf_counter() - t0
+        same = bool(res[0]) and bool(ref) and res[0][0][3].yseq.tolist() == ref[0][3].yseq.tolist()
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "utterances/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"1 utterance of {secs} s (utt 0 of the batch), batch-1, no warm-up",
+                                "best_hyp_matches_gpu": same}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="conformer_large_joint_64x30s", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -170,6 +170,14 @@ class Speech2Text:
         return [self._results(h) for h in hyps]
 
     @torch.no_grad()
+    def batch_decode_padded(self, speech: torch.Tensor, lengths: torch.Tensor):
+        """Pre-batched input: speech (B, Lmax) float32 (pinned host or device memory), lengths (B,) -> as batch_decode."""
+        speech = speech.to(self.device, non_blocking=True)
+        enc, enc_lens = self.asr_model.encode(speech, lengths)
+        hyps = self.beam_search.forward_batch(enc, enc_lens, self.asr_model.enc_split(enc), self.maxlenratio, self.minlenratio)
+        return [self._results(h) for h in hyps]
+
+    @torch.no_grad()
     def __call__(self, speech: Union[torch.Tensor, np.ndarray]):
         logger.info("speech length: " + str(int(speech.shape[0])))
         return self.batch_decode([speech])[0]

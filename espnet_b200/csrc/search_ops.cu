@@ -138,8 +138,11 @@ __global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restri
     }
   }
   __syncthreads();           // scores no longer needed: reuse `red`
-  if (g < ngrp)
-    for (int w = 0; w < W; ++w) red[((long long)g * W + w) * dk + d] = acc[w];
+  if (g < ngrp) {
+#pragma unroll
+    for (int w = 0; w < 16; ++w)
+      if (w < W) red[((long long)g * W + w) * dk + d] = acc[w];
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < W * dk; i += blockDim.x) {
     float a = 0.f;
@@ -456,7 +459,7 @@ int espb_dec_self_attn_f32(const float* qkv, float* kc, float* vc, const int* an
 int espb_dec_src_attn_f32(const float* q, const float* kv, long long kv_ld, int k_off, int v_off, int U, int Tmax, const int* lens, int W, int D,
                           int H, float* ctx, long long ctx_plane, cudaStream_t stream) {
   const int dk = D / H;
-  if (W > 16 || dk > 256 || (dk & 3) || 256 % dk) { espb_set_error("dec_src_attn: needs beam <= 16 and d_k in {4..256} dividing 256"); return ESPB_ERR_ARG; }
+  if (W > 16 || dk > 256 || (dk & 3)) { espb_set_error("dec_src_attn: needs beam <= 16 and d_k a multiple of 4, <= 256"); return ESPB_ERR_ARG; }
   const int ngrp = 256 / dk;
   const size_t smem = ((size_t)W * dk + (size_t)W * Tmax + (size_t)ngrp * W * dk) * sizeof(float);
   if (smem > 200 * 1024) { espb_set_error("dec_src_attn: beam*T too large for shared memory"); return ESPB_ERR_ARG; }

@@ -15,6 +15,7 @@ ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2
 # tensor-core GEMM unless ESPNET_B200_GEMM=simt (bring-up / A-B checks); shapes TMA cannot address use SIMT.
 _GEMM_MODE = os.environ.get("ESPNET_B200_GEMM", "tc")
 launch_counter = [0]
+gemm_profile = None  # set to a list to record (algorithmic flops, start event, end event) per tensor-core GEMM launch
 
 
 def set_gemm_mode(mode):
@@ -73,7 +74,14 @@ def gemm(M, N, K, A, a_plane, lda, B, b_plane, ldb, C, ldc, *, c_plane=0, split_
             use_tc = False
         if a_mode == 0 and kob > 0 and K % (kob * 32):
             use_tc = False
+    prof = gemm_profile if use_tc else None
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("espb_gemm_f32", d, 1 if use_tc else 0)
+    if prof is not None:
+        e1.record()
+        prof.append((2.0 * M * N * K * nbx * nby, e0, e1))
     _count()
     return use_tc
 
