@@ -248,6 +248,223 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------ tensor-core kernel v2: CTA pair + chunked promotion
+// cta_group::2: a cluster of two CTAs computes a 256 x BN tile (UMMA M=256); each CTA stages its own 128 rows of A and
+// its half (BN/2 rows) of B, so per-SM L2->smem traffic per MMA is halved against the 1-CTA kernel. The fp32 accumulator of
+// the tensor core truncates on every accumulation step, so K is walked in chunks of CHUNK_KB k-blocks that accumulate in
+// one of two TMEM buffers (restart with accumulate=0) while 8 epilogue warps add the previous chunk into fp32 registers
+// with round-to-nearest: the long accumulation chain runs on CUDA cores, the products on tensor cores.
+//   warp 0: TMA producer (each CTA loads its halves; both signal the leader CTA's full barrier)
+//   warp 1: TMEM alloc (both CTAs) + MMA issue (leader CTA only)
+//   warps 2-9: epilogue; warp e owns TMEM lanes 32*(e%4).. and columns (e/4)*BN/2 ..
+constexpr int V2_THREADS = 320;
+constexpr int CHUNK_KB = 4;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm(uint32_t bar) {  // arrive on the barrier at this offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t target_rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(local_bar), "r"(target_rank)
+      : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
+gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym) {
+  constexpr int BH = BN / 2;                      // B rows staged by each CTA
+  constexpr int B_TILE_BYTES = BH * 128;
+  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  constexpr int CW = BN / 2;                      // accumulator columns per epilogue warp
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * STAGES;
+  const uint32_t tfull_bar = bar_base + 16 * STAGES, tempty_bar = tfull_bar + 16;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 16 * STAGES + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int m0 = pair * 256 + (int)rank * 128;
+  const int n0 = blockIdx.y * BN;
+  const int bx = blockIdx.z % p.nbx, by = blockIdx.z / p.nbx;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 16); }  // 8 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int cblk = (p.a_mode == 1) ? p.cv_cin / BK : 0;
+      const uint32_t leader_full = full_bar & 0xFEFFFFFFu;   // same offset in the even (leader) CTA of the pair
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        if (leader) mbar_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);  // bytes of both CTAs land on the leader's barrier
+        const uint32_t fb = leader_full + 8 * s;
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        if (p.a_mode == 0) {
+          const int ko = (p.kob > 0) ? kb / p.kob : 0;
+          const int ki = (p.kob > 0) ? kb % p.kob : kb;
+          tma_load_5d_2sm(sa, &tmA, fb, ki * BK, m0, bx + ko, by, 0);
+          tma_load_5d_2sm(sa + A_TILE_BYTES, &tmA, fb, ki * BK, m0, bx + ko, by, 1);
+        } else {
+          const int tap = kb / cblk, c0 = (kb % cblk) * BK;
+          const int kt = tap / 3, kf = tap % 3;
+          const int par = (kt & 1) * 2 + (kf & 1);
+          tma_load_5d_2sm(sa, &tmA, fb, c0, m0 + (kt >> 1), bx + (kf >> 1), par, by);
+          tma_load_5d_2sm(sa + A_TILE_BYTES, &tmA, fb, c0, m0 + (kt >> 1), bx + (kf >> 1), 4 + par, by);
+        }
+        const int nb = n0 + (int)rank * BH;
+        tma_load_5d_2sm(sa + 2 * A_TILE_BYTES, &tmB, fb, kb * BK, nb, bx * bxm, by * bym, 0);
+        tma_load_5d_2sm(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB, fb, kb * BK, nb, bx * bxm, by * bym, 1);
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      for (int c = 0; c < num_chunks; ++c) {
+        const int b = c & 1;
+        mbar_wait(tempty_bar + 8 * b, ((c >> 1) & 1) ^ 1);   // both CTAs' epilogues have drained this accumulator buffer
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(b * BN);
+        const int kb_end = min(num_kb, (c + 1) * CHUNK_KB);
+        for (int kb = c * CHUNK_KB; kb < kb_end; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(full_bar + 8 * s, ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
+            const uint64_t b_hi = umma_desc(sa + 2 * A_TILE_BYTES + k * 32);
+            const uint64_t b_lo = umma_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + k * 32);
+            mma_tf32_2sm(d, a_lo, b_hi, idesc, (kb != c * CHUNK_KB || k != 0) ? 1u : 0u);
+            mma_tf32_2sm(d, a_hi, b_lo, idesc, 1);
+            mma_tf32_2sm(d, a_hi, b_hi, idesc, 1);
+          }
+          tcgen05_commit_2sm(empty_bar + 8 * s);
+        }
+        tcgen05_commit_2sm(tfull_bar + 8 * b);
+      }
+    }
+  } else {
+    const int e = warp - 2, q = warp & 3, half = e >> 2;   // a warp may only touch TMEM lanes 32*(warp_id%4)..+31
+    float acc[CW];
+#pragma unroll
+    for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+    for (int c = 0; c < num_chunks; ++c) {
+      const int b = c & 1;
+      mbar_wait(tfull_bar + 8 * b, (c >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int j = 0; j < CW / 32; ++j) {
+        float v[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + half * CW + j * 32), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * b, 0);   // leader CTA's barrier (local or remote)
+    }
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    EpiArgs ea;
+    const long long coff = (long long)by * p.sc_y + (long long)bx * p.sc_x;
+    ea.C = p.C + coff; ea.c_plane = p.c_plane; ea.ldc = p.ldc; ea.split_out = p.split_out;
+    ea.bias = p.bias; ea.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
+    ea.ldr = p.ldr; ea.alpha = p.alpha; ea.act = p.act;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((coff & 3) == 0) && ((p.c_plane & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    if (row_ok) {
+      float* crow = ea.C + (long long)row * ea.ldc;
+      const int colbase = n0 + half * CW;
+#pragma unroll
+      for (int j = 0; j < CW; j += 4) {
+        const int col0 = colbase + j;
+        if (col0 >= p.N) continue;
+        if (vec_ok && col0 + 4 <= p.N) {
+          float t0 = epi_value(ea, acc[j], row, col0), t1 = epi_value(ea, acc[j + 1], row, col0 + 1);
+          float t2 = epi_value(ea, acc[j + 2], row, col0 + 2), t3 = epi_value(ea, acc[j + 3], row, col0 + 3);
+          float4 o, l;
+          if (ea.split_out) {
+            o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
+            l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
+            *reinterpret_cast<float4*>(crow + col0) = o;
+            *reinterpret_cast<float4*>(crow + ea.c_plane + col0) = l;
+          } else {
+            o.x = t0; o.y = t1; o.z = t2; o.w = t3;
+            *reinterpret_cast<float4*>(crow + col0) = o;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int col = col0 + i;
+            if (col < p.N) {
+              float t = epi_value(ea, acc[j + i], row, col);
+              if (ea.split_out) { float h = espb::tf32_hi(t); crow[col] = h; crow[ea.c_plane + col] = espb::tf32_lo(t, h); }
+              else crow[col] = t;
+            }
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still read this CTA's smem / signal its barriers until both are done
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ SIMT kernel (fp32 FFMA)
 __device__ __forceinline__ float load_a(const EspbGemmDesc& p, int bx, int by, int m, int k) {
   if (m >= p.M || k >= p.K) return 0.f;
@@ -383,9 +600,26 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc
   return ESPB_OK;
 }
 
+template <int BN, int STAGES>
+int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, cudaStream_t stream) {
+  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * (BN / 2) * 128) + 1024 + 16 * STAGES + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tf32x3_2cta_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      espb_set_error("cudaFuncSetAttribute(max dynamic smem) failed");
+      return ESPB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(2 * ((d.M + 255) / 256), (d.N + BN - 1) / BN, d.nbx * d.nby);
+  gemm_tf32x3_2cta_kernel<BN, STAGES><<<grid, V2_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
 }  // namespace
 
-int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream) {
+int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version) {
   if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.nbx <= 0 || d.nby <= 0) { espb_set_error("gemm: bad shape"); return ESPB_ERR_ARG; }
   CUtensorMap tmA, tmB;
   int rc;
@@ -405,6 +639,16 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream) {
   if (rc != ESPB_OK) return rc;
   const int bxm = d.sb_x != 0 ? 1 : 0, bym = d.sb_y != 0 ? 1 : 0;
   const long long tiles_m = (d.M + BM - 1) / BM, nb = (long long)d.nbx * d.nby;
+  if (version == 2) {
+    // CTA-pair kernel: 256 x BN tiles; B box = BN/2 rows per CTA
+    const int bn = (d.N <= 128) ? 128 : 256;
+    long long dims[5] = {d.K, d.N, bxm ? d.nbx : 1, bym ? d.nby : 1, 2};
+    long long str[4] = {d.ldb, d.sb_x, d.sb_y, d.b_plane};
+    rc = make_map(&tmB, d.B, dims, str, bn / 2);
+    if (rc != ESPB_OK) return rc;
+    if (bn == 256) return launch_tc2<256, 3>(tmA, tmB, d, bxm, bym, stream);
+    return launch_tc2<128, 4>(tmA, tmB, d, bxm, bym, stream);
+  }
   int bn;
   if (d.N <= 64) bn = 64;
   else if (d.N <= 128) bn = 128;

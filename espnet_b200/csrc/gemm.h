@@ -26,5 +26,5 @@ struct EspbGemmDesc {
   int cv_t1h, cv_f1h, cv_cin;  // mode 1: conv1-output half extents and channel count
 };
 
-int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream);    // tcgen05, needs 16B-aligned strides
+int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version);  // tcgen05 (1: 1-CTA, 2: CTA pair + chunked promotion)
 int espb_gemm_simt_launch(const EspbGemmDesc& d, cudaStream_t stream);  // any strides

@@ -12,7 +12,8 @@ from .lib import GemmDesc, call, ptr
 
 ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2
 
-# tensor-core GEMM unless ESPNET_B200_GEMM=simt (bring-up / A-B checks); shapes TMA cannot address use SIMT.
+# GEMM kernel: "tc" = tcgen05 1-CTA, "tc2" = tcgen05 CTA pair + chunked fp32 promotion, "simt" = FFMA (bring-up / A-B checks);
+# shapes TMA cannot address always use SIMT.
 _GEMM_MODE = os.environ.get("ESPNET_B200_GEMM", "tc")
 launch_counter = [0]
 gemm_profile = None  # set to a list to record (algorithmic flops, start event, end event) per tensor-core GEMM launch
@@ -20,7 +21,7 @@ gemm_profile = None  # set to a list to record (algorithmic flops, start event, 
 
 def set_gemm_mode(mode):
     global _GEMM_MODE
-    assert mode in ("tc", "simt")
+    assert mode in ("tc", "tc2", "simt")
     _GEMM_MODE = mode
 
 
@@ -64,26 +65,26 @@ def gemm(M, N, K, A, a_plane, lda, B, b_plane, ldb, C, ldc, *, c_plane=0, split_
     d.alpha, d.act = float(alpha), act
     d.cv_t1h, d.cv_f1h, d.cv_cin = conv
     mode = force or _GEMM_MODE
-    use_tc = mode == "tc"
+    use_tc = {"tc": 1, "tc2": 2}.get(mode, 0)
     if use_tc:
         # TMA needs 16-byte aligned bases and strides
         al = [lda, ldb, a_plane, b_plane, sa[0], sa[1], sb[0], sb[1], a_off, b_off]
         if any(v % 4 for v in al):
-            use_tc = False
+            use_tc = 0
         if a_mode == 1 and conv[2] % 32:
-            use_tc = False
+            use_tc = 0
         if a_mode == 0 and kob > 0 and K % (kob * 32):
-            use_tc = False
+            use_tc = 0
     prof = gemm_profile if use_tc else None
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    call("espb_gemm_f32", d, 1 if use_tc else 0)
+    call("espb_gemm_f32", d, use_tc)
     if prof is not None:
         e1.record()
         prof.append((2.0 * M * N * K * nbx * nby, e0, e1))
     _count()
-    return use_tc
+    return bool(use_tc)
 
 
 def linear(x_split, w_split, out, *, bias=None, act=ACT_NONE, residual=None, alpha=1.0, split_out=False, force=None):

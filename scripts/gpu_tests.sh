@@ -10,6 +10,8 @@ for st in $stages; do
   case $st in
     gemm_simt) mode=simt; file=tests/test_gpu_gemm.py;;
     gemm_tc)   mode=tc;   file=tests/test_gpu_gemm.py;;
+    gemm_tc2)  mode=tc2;  file=tests/test_gpu_gemm.py;;
+    pipe_tc2)  mode=tc2;  file=tests/test_gpu_pipeline.py;;
     pipe_simt) mode=simt; file=tests/test_gpu_pipeline.py;;
     pipe_tc)   mode=tc;   file=tests/test_gpu_pipeline.py;;
     *) echo "unknown stage $st"; continue;;
