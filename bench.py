@@ -240,6 +240,27 @@ def run_b200(args, rank, local_rank, world):
     speech_dev = host.to(dev)
     for _ in range(args.warmup):
         step_resident(speech_dev)
+    if args.breakdown:   # per-launch CUDA-event timing of one step, aggregated by kernel (and GEMM shape) -> stderr
+        from espnet_b200 import lib as _lib
+        import collections
+
+        _lib.profile = []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_resident(speech_dev)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        prof, _lib.profile = _lib.profile, None
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for name, tag, e0, e1 in prof:
+            k = name.replace("espb_", "") + (" " + tag if tag else "")
+            agg[k][0] += 1
+            agg[k][1] += e0.elapsed_time(e1)
+        tot = sum(v[1] for v in agg.values())
+        print(f"[breakdown] {args.workload}: {len(prof)} launches, sum of kernel times {tot:.1f} ms, wall {wall * 1e3:.1f} ms", file=sys.stderr)
+        for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+            print(f"[breakdown] {100 * ms / tot:6.2f}%  {ms:9.3f} ms  {c:5d}x  avg {1e3 * ms / c:9.1f} us  {k}", file=sys.stderr)
+        return
     if args.profile_one_step:   # for ncu --profile-from-start off: exactly one resident step inside the profiler range
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -336,6 +357,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="conformer_large_joint_64x30s", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--breakdown", action="store_true", help="time every launch of one step with CUDA events and print a per-kernel table")
     ap.add_argument("--profile-one-step", action="store_true", help="warm up, then run one step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -112,6 +112,18 @@ def stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+profile = None  # set to a list to record (name, tag, start_event, end_event) for every launch (bench --breakdown)
+profile_tag = [""]
+
+
 def call(name, *args):
     lib = load()
+    if profile is None:
+        check(getattr(lib, name)(*args, stream()), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib, name)(*args, stream()), name)
+    e1.record()
+    profile.append((name, profile_tag[0], e0, e1))
+    profile_tag[0] = ""

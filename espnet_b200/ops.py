@@ -75,6 +75,8 @@ def gemm(M, N, K, A, a_plane, lda, B, b_plane, ldb, C, ldc, *, c_plane=0, split_
             use_tc = 0
         if a_mode == 0 and kob > 0 and K % (kob * 32):
             use_tc = 0
+    if lib.profile is not None:
+        lib.profile_tag[0] = f"{'tc' + str(use_tc) if use_tc else 'simt'} M{M} N{N} K{K} x{nbx * nby}" + (" conv" if a_mode else "")
     prof = gemm_profile if use_tc else None
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
