@@ -31,7 +31,8 @@ __global__ void dec_embed_kernel(const int* __restrict__ last_tok, const float* 
 
 // ---------------------------------------------------------------- self-attention of the newest token over the prefix
 // qkv [n][3D] (this step's q,k,v, bias added). K/V of earlier positions j < pos live in kc/vc [Lmax][n][D] at slot anc[s][j].
-// Writes this step's k,v into kc/vc[pos][s] and ctx (split) [n][D].  One warp per (slot, head); d_k <= 128.
+// Writes this step's k,v into kc/vc[pos][s] and ctx (split) [n][D].  One warp per (slot, head); lanes split d_k (<= 128) so
+// that every K/V row is one coalesced read; 4 positions are in flight per iteration.
 __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc,
                                                             const int* __restrict__ anc, int anc_ld, int n, int D, int H, int pos,
                                                             float* __restrict__ ctx, long long ctx_plane) {
@@ -42,19 +43,41 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
   const int s = wid / H, h = wid % H, dk = D / H;
   float* sc = sm + warp * (pos + 1);
   const float* q = qkv + (long long)s * 3 * D + h * dk;
-  const float* kn = q + D;
-  const float* vn = q + 2 * D;
-  // append this step's k, v to the cache
-  for (int d = lane; d < dk; d += 32) {
-    kc[((long long)pos * n + s) * D + h * dk + d] = kn[d];
-    vc[((long long)pos * n + s) * D + h * dk + d] = vn[d];
+  float qr[4], kn[4], vn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    qr[i] = (d < dk) ? q[d] : 0.f;
+    kn[i] = (d < dk) ? q[D + d] : 0.f;
+    vn[i] = (d < dk) ? q[2 * D + d] : 0.f;
+    if (d < dk) {   // append this step's k, v to the cache
+      kc[((long long)pos * n + s) * D + h * dk + d] = kn[i];
+      vc[((long long)pos * n + s) * D + h * dk + d] = vn[i];
+    }
   }
   const float rs = sqrtf((float)dk);
-  for (int j = lane; j <= pos; j += 32) {
-    const float* kj = (j == pos) ? kn : kc + ((long long)j * n + anc[(long long)s * anc_ld + j]) * D + h * dk;
-    float a = 0.f;
-    for (int d = 0; d < dk; ++d) a = fmaf(q[d], kj[d], a);
-    sc[j] = a / rs;
+  const int* an = anc + (long long)s * anc_ld;
+  for (int j0 = 0; j0 <= pos; j0 += 4) {
+    float part[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      float a = 0.f;
+      if (j < pos) {
+        const float* kj = kc + ((long long)j * n + an[j]) * D + h * dk;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const int d = lane + 32 * i; if (d < dk) a = fmaf(qr[i], kj[d], a); }
+      } else if (j == pos) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a = fmaf(qr[i], kn[i], a);
+      }
+      part[u] = a;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float a = espb::warp_sum(part[u]);
+      if (lane == 0 && j0 + u <= pos) sc[j0 + u] = a / rs;
+    }
   }
   __syncwarp();
   float mx = -INFINITY;
@@ -64,13 +87,22 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
   for (int j = lane; j <= pos; j += 32) { float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
   sum = espb::warp_sum(sum);
   __syncwarp();
-  for (int d = lane; d < dk; d += 32) {
-    float a = 0.f;
-    for (int j = 0; j <= pos; ++j) {
-      const float* vj = (j == pos) ? vn : vc + ((long long)j * n + anc[(long long)s * anc_ld + j]) * D + h * dk;
-      a = fmaf(sc[j] / sum, vj[d], a);
-    }
-    store_split(ctx + (long long)s * D + h * dk + d, ctx_plane, a);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < pos; ++j) {
+    const float pj = sc[j] / sum;
+    const float* vj = vc + ((long long)j * n + an[j]) * D + h * dk;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int d = lane + 32 * i; if (d < dk) acc[i] = fmaf(pj, vj[d], acc[i]); }
+  }
+  {
+    const float pj = sc[pos] / sum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = fmaf(pj, vn[i], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < dk) store_split(ctx + (long long)s * D + h * dk + d, ctx_plane, acc[i]);
   }
 }
 
@@ -79,7 +111,7 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
 __global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, long long kv_ld, int k_off,
                                                            int v_off, int Tmax, const int* __restrict__ lens, int W, int D, int H,
                                                            float* __restrict__ ctx, long long ctx_plane) {
-  extern __shared__ float sm[];  // q [W][dk] | scores [W][T] | red [4][W][dk]
+  extern __shared__ float sm[];  // q [W][dk] | scores [W][Tmax] | red [nwarp][W][dk]
   const int u = blockIdx.x / H, h = blockIdx.x % H, dk = D / H;
   const int T = lens[u];
   float* qs = sm;
@@ -123,30 +155,41 @@ __global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restri
     for (int t = lane; t < T; t += 32) r[t] = r[t] / sum;
   }
   __syncthreads();
-  // ctx[w][d] = sum_t p[w][t] * V[t][d]; thread = (d, t-group)
-  const int ngrp = blockDim.x / dk;  // dk in {16,32,64,128}; blockDim 256 -> >= 2 groups
-  const int d = threadIdx.x % dk, g = threadIdx.x / dk;
-  float acc[16];
+  // ctx[w][d] = sum_t p[w][t] * V[t][d]: warps split t, lanes split d (coalesced V rows), 8 rows in flight per warp
+  {
+    constexpr int UN = 8;
+    const int nd = (dk + 31) / 32;               // d values per lane (dk <= 256 -> <= 8); common case dk=64 -> 2
+    for (int dd = 0; dd < nd; ++dd) {
+      const int d = lane + 32 * dd;
+      float acc[16];
 #pragma unroll
-  for (int w = 0; w < 16; ++w) acc[w] = 0.f;
-  if (g < ngrp) {
-    for (int t = g; t < T; t += ngrp) {
-      const float vv = vbase[(long long)t * kv_ld + d];
+      for (int w = 0; w < 16; ++w) acc[w] = 0.f;
+      for (int t0 = warp * UN; t0 < T; t0 += nwarp * UN) {
+        float vv[UN];
 #pragma unroll
-      for (int w = 0; w < 16; ++w)
-        if (w < W) acc[w] = fmaf(sc[w * Tmax + t], vv, acc[w]);
+        for (int uu = 0; uu < UN; ++uu) {
+          const int t = t0 + uu;
+          vv[uu] = (t < T && d < dk) ? vbase[(long long)t * kv_ld + d] : 0.f;
+        }
+#pragma unroll
+        for (int uu = 0; uu < UN; ++uu) {
+          const int t = min(t0 + uu, T - 1);
+#pragma unroll
+          for (int w = 0; w < 16; ++w)
+            if (w < W) acc[w] = fmaf(sc[w * Tmax + t], vv[uu], acc[w]);
+        }
+      }
+      if (d < dk) {
+#pragma unroll
+        for (int w = 0; w < 16; ++w)
+          if (w < W) red[((long long)warp * W + w) * dk + d] = acc[w];
+      }
     }
-  }
-  __syncthreads();           // scores no longer needed: reuse `red`
-  if (g < ngrp) {
-#pragma unroll
-    for (int w = 0; w < 16; ++w)
-      if (w < W) red[((long long)g * W + w) * dk + d] = acc[w];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < W * dk; i += blockDim.x) {
     float a = 0.f;
-    for (int gg = 0; gg < ngrp; ++gg) a += red[(long long)gg * W * dk + i];
+    for (int gg = 0; gg < nwarp; ++gg) a += red[(long long)gg * W * dk + i];
     store_split(ctx + ((long long)(u * W + i / dk)) * D + h * dk + (i % dk), ctx_plane, a);
   }
 }
@@ -206,76 +249,74 @@ __global__ void ctc_init_state_kernel(const float* __restrict__ logp, int Tmax, 
   s_prev[s] = 0.f;
 }
 
-struct CtcRec {  // one forward recursion for prefix g of slot s extended by token c
-  float log_psi;
-};
+// log_phi[t] of the previous state: r_sum unless the candidate repeats the last label (ctc_prefix_score.py:135-144).
+__device__ __forceinline__ float ctc_phi(const float* __restrict__ rp, int t, bool same) {
+  const float p0 = rp[2 * t], p1 = rp[2 * t + 1];
+  return same ? p1 : logaddexp(p0, p1);
+}
 
-// Runs the recursion of ctc_prefix_score.py:128-182 for one (slot, token). If r_out != null the new
-// forward variables r_out[t][0..1] are stored (state of the extended prefix).
-__device__ __forceinline__ float ctc_prefix_recursion(const float* __restrict__ x /* logp of utt: [T][V] */, int V, int T, int blank, int eos,
-                                                      const float* __restrict__ rp /* [T][2] */, int c, int last, int out_len,
-                                                      float* __restrict__ r_out, int Tmax) {
-  if (c == eos) {  // (:184-185) log_psi[eos] = r_sum[T-1]
-    if (r_out) for (int t = 0; t < Tmax; ++t) { r_out[2 * t] = LOGZERO; r_out[2 * t + 1] = LOGZERO; }
-    return logaddexp(rp[2 * (T - 1)], rp[2 * (T - 1) + 1]);
-  }
+// log_psi of extending the prefix of a slot by token c (ctc_prefix_score.py:166-189).  It depends only on the PREVIOUS state:
+//   log_psi = logsumexp( {log_phi[t-1] + x[t,c]}_{t=start..T-1}, r[start-1,0] ),   r[start-1,0] = x[0,c] if the prefix is empty else logzero
+// so it is a reduction over t: one warp per (slot, candidate), lanes stride t.  Must be called by a full warp.
+__device__ __forceinline__ float ctc_log_psi_warp(const float* __restrict__ x, int V, int T, int blank, int eos, const float* __restrict__ rp, int c,
+                                                  int last, int out_len, int lane) {
+  if (c == eos) return logaddexp(rp[2 * (T - 1)], rp[2 * (T - 1) + 1]);   // (:184-185)
+  if (c == blank) return LOGZERO;                                          // (:187-189)
   const int start = max(out_len, 1);
-  float rn = LOGZERO, rb = LOGZERO;
-  if (out_len == 0) rn = x[c];  // r[0,0] = x[0,c]
-  if (r_out) {
-    for (int t = 0; t < start - 1; ++t) { r_out[2 * t] = LOGZERO; r_out[2 * t + 1] = LOGZERO; }
-    r_out[2 * (start - 1)] = rn; r_out[2 * (start - 1) + 1] = rb;
-  }
-  // log_psi = logsumexp( {log_phi[t-1] + x[t,c]}_{t=start..T-1}, r[start-1,0] ): streaming max/sum
-  float m = rn, ssum = 1.f;  // first element r[start-1,0]
   const bool same = (c == last);
-  for (int t = start; t < T; ++t) {
-    const float p0 = rp[2 * (t - 1)], p1 = rp[2 * (t - 1) + 1];
-    const float phi = same ? p1 : logaddexp(p0, p1);
-    const float xc = x[(long long)t * V + c], xb = x[(long long)t * V + blank];
-    const float nrn = logaddexp(rn, phi) + xc;
-    const float nrb = logaddexp(rn, rb) + xb;
-    rn = nrn; rb = nrb;
-    if (r_out) { r_out[2 * t] = rn; r_out[2 * t + 1] = rb; }
-    const float e = phi + xc;
-    if (e > m) { ssum = ssum * expf(m - e) + 1.f; m = e; } else { ssum += expf(e - m); }
-  }
-  if (r_out) for (int t = T; t < Tmax; ++t) { r_out[2 * t] = LOGZERO; r_out[2 * t + 1] = LOGZERO; }
-  float psi = m + logf(ssum);
-  if (c == blank) psi = LOGZERO;  // (:187-189)
-  return psi;
+  const float r0 = (out_len == 0) ? x[c] : LOGZERO;
+  float m = -INFINITY;
+  for (int t = start + lane; t < T; t += 32) m = fmaxf(m, ctc_phi(rp, t - 1, same) + x[(long long)t * V + c]);
+  m = fmaxf(espb::warp_max(m), r0);
+  float ssum = 0.f;
+  for (int t = start + lane; t < T; t += 32) ssum += expf(ctc_phi(rp, t - 1, same) + x[(long long)t * V + c] - m);
+  ssum = espb::warp_sum(ssum) + expf(r0 - m);
+  return m + logf(ssum);
 }
 
 // Scores for candidate lists: cand [n][P] (from the pre-beam) plus eos as candidate P. Outputs part[n][P+1] = log_psi - s_prev
-// and psi[n][P+1]. Duplicate eos (eos already among the P) is flagged by valid[n][P+1] = 0.
-__global__ void __launch_bounds__(128) ctc_score_cands_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank,
+// and psi[n][P+1]. Duplicate eos (eos already among the P) is flagged by valid[n][P+1] = 0.  One warp per (slot, candidate).
+__global__ void __launch_bounds__(256) ctc_score_cands_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank,
                                                               int eos, int W, int n, const float* __restrict__ r_prev, const float* __restrict__ s_prev,
                                                               const int* __restrict__ last_tok, int out_len, const int* __restrict__ cand, int P,
                                                               float* __restrict__ part, float* __restrict__ psi, int* __restrict__ valid) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (idx >= n * (P + 1)) return;
   const int s = idx / (P + 1), j = idx % (P + 1);
   const int u = s / W;
-  int c = (j < P) ? cand[(long long)s * P + j] : eos;
+  const int c = (j < P) ? cand[(long long)s * P + j] : eos;
   int ok = 1;
   if (j == P) for (int q = 0; q < P; ++q) if (cand[(long long)s * P + q] == eos) ok = 0;
-  const float v = ctc_prefix_recursion(logp + (long long)u * Tmax * V, V, lens[u], blank, eos, r_prev + (long long)s * Tmax * 2, c, last_tok[s],
-                                       out_len, nullptr, Tmax);
-  psi[idx] = v;
-  part[idx] = v - s_prev[s];
-  valid[idx] = ok;
+  const float v = ctc_log_psi_warp(logp + (long long)u * Tmax * V, V, lens[u], blank, eos, r_prev + (long long)s * Tmax * 2, c, last_tok[s],
+                                   out_len, lane);
+  if (lane == 0) { psi[idx] = v; part[idx] = v - s_prev[s]; valid[idx] = ok; }
 }
 
-// Dense variant (ctc_weight == 1: no pre-beam, ctc_prefix_score.py:118-122): part[n][V].
+// Dense variant (ctc_weight == 1: no pre-beam, ctc_prefix_score.py:118-122): part[n][V].  One thread per (slot, token); adjacent
+// threads read adjacent tokens of a frame (coalesced), streaming log-sum-exp over t.
 __global__ void __launch_bounds__(128) ctc_score_dense_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank,
                                                               int eos, int W, int n, const float* __restrict__ r_prev, const float* __restrict__ s_prev,
                                                               const int* __restrict__ last_tok, int out_len, float* __restrict__ part) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n * V) return;
   const int s = (int)(idx / V), c = (int)(idx % V);
-  const int u = s / W;
-  const float v = ctc_prefix_recursion(logp + (long long)u * Tmax * V, V, lens[u], blank, eos, r_prev + (long long)s * Tmax * 2, c, last_tok[s],
-                                       out_len, nullptr, Tmax);
+  const int u = s / W, T = lens[u];
+  const float* x = logp + (long long)u * Tmax * V;
+  const float* rp = r_prev + (long long)s * Tmax * 2;
+  float v;
+  if (c == eos) v = logaddexp(rp[2 * (T - 1)], rp[2 * (T - 1) + 1]);
+  else if (c == blank) v = LOGZERO;
+  else {
+    const int start = max(out_len, 1);
+    const bool same = (c == last_tok[s]);
+    float m = (out_len == 0) ? x[c] : LOGZERO, ssum = 1.f;
+    for (int t = start; t < T; ++t) {
+      const float e = ctc_phi(rp, t - 1, same) + x[(long long)t * V + c];
+      if (e > m) { ssum = ssum * expf(m - e) + 1.f; m = e; } else { ssum += expf(e - m); }
+    }
+    v = m + logf(ssum);
+  }
   part[idx] = v - s_prev[s];
 }
 
@@ -407,25 +448,52 @@ __global__ void anc_update_kernel(const int* __restrict__ anc, int* __restrict__
   if (threadIdx.x == 0) n_anc[(long long)s * anc_ld + pos] = p;
 }
 
-// New CTC forward variables of each surviving slot: recursion for (parent state, chosen token), storing r.
-__global__ void __launch_bounds__(32) ctc_advance_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank, int eos,
-                                                         int W, int n, const float* __restrict__ r_prev, const int* __restrict__ parent,
-                                                         const int* __restrict__ par_last_tok, const int* __restrict__ new_tok,
-                                                         const int* __restrict__ new_active, int out_len, float* __restrict__ r_new,
-                                                         float* __restrict__ s_new) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// New CTC forward variables of each surviving slot: the recursion of ctc_prefix_score.py:128-164 for (parent state, chosen token),
+// storing r[t][0..1].  One warp per slot: lanes prefetch 32 frames of (log_phi, x[t,c], x[t,blank]) in parallel, then the warp walks
+// the 32 sequential steps with shuffles (the dependent chain is two logaddexp per frame); lane l keeps frame l for a coalesced store.
+__global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank, int eos,
+                                                          int W, int n, const float* __restrict__ r_prev, const int* __restrict__ parent,
+                                                          const int* __restrict__ par_last_tok, const int* __restrict__ new_tok,
+                                                          const int* __restrict__ new_active, int out_len, float* __restrict__ r_new,
+                                                          float* __restrict__ s_new) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (s >= n) return;
   const int u = s / W;
-  float* ro = r_new + (long long)s * Tmax * 2;
-  if (!new_active[s]) {
-    for (int t = 0; t < Tmax; ++t) { ro[2 * t] = LOGZERO; ro[2 * t + 1] = LOGZERO; }
-    s_new[s] = 0.f;
+  float2* ro = reinterpret_cast<float2*>(r_new + (long long)s * Tmax * 2);
+  const int c = new_tok[s];
+  if (!new_active[s] || c == eos || c == blank) {   // ended / inactive hypotheses never use their state again
+    for (int t = lane; t < Tmax; t += 32) ro[t] = make_float2(LOGZERO, LOGZERO);
+    if (lane == 0) s_new[s] = 0.f;
     return;
   }
-  const int p = parent[s];
-  const float psi = ctc_prefix_recursion(logp + (long long)u * Tmax * V, V, lens[u], blank, eos, r_prev + (long long)p * Tmax * 2, new_tok[s],
-                                         par_last_tok[p], out_len, ro, Tmax);
-  s_new[s] = psi;
+  const int p = parent[s], T = lens[u];
+  const float* x = logp + (long long)u * Tmax * V;
+  const float* rp = r_prev + (long long)p * Tmax * 2;
+  const int last = par_last_tok[p];
+  const bool same = (c == last);
+  const int start = max(out_len, 1);
+  float rn = (out_len == 0) ? x[c] : LOGZERO, rb = LOGZERO;   // r[start-1]
+  for (int t = lane; t < start - 1; t += 32) ro[t] = make_float2(LOGZERO, LOGZERO);
+  if (lane == 0) ro[start - 1] = make_float2(rn, rb);
+  for (int t0 = start; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    float phi = LOGZERO, xc = 0.f, xb = 0.f;
+    if (t < T) { phi = ctc_phi(rp, t - 1, same); xc = x[(long long)t * V + c]; xb = x[(long long)t * V + blank]; }
+    float my_n = LOGZERO, my_b = LOGZERO;
+    const int cnt = min(32, T - t0);
+    for (int i = 0; i < cnt; ++i) {
+      const float ph = __shfl_sync(0xffffffffu, phi, i), c1 = __shfl_sync(0xffffffffu, xc, i), b1 = __shfl_sync(0xffffffffu, xb, i);
+      const float nrn = logaddexp(rn, ph) + c1;
+      const float nrb = logaddexp(rn, rb) + b1;
+      rn = nrn; rb = nrb;
+      if (lane == i) { my_n = rn; my_b = rb; }
+    }
+    if (t < T) ro[t] = make_float2(my_n, my_b);
+  }
+  for (int t = T + lane; t < Tmax; t += 32) ro[t] = make_float2(LOGZERO, LOGZERO);
+  const float psi = ctc_log_psi_warp(x, V, T, blank, eos, rp, c, last, out_len, lane);
+  if (lane == 0) s_new[s] = psi;
 }
 
 __global__ void count_active_kernel(const int* __restrict__ active, int n, int* __restrict__ out) {
@@ -460,8 +528,7 @@ int espb_dec_src_attn_f32(const float* q, const float* kv, long long kv_ld, int 
                           int H, float* ctx, long long ctx_plane, cudaStream_t stream) {
   const int dk = D / H;
   if (W > 16 || dk > 256 || (dk & 3)) { espb_set_error("dec_src_attn: needs beam <= 16 and d_k a multiple of 4, <= 256"); return ESPB_ERR_ARG; }
-  const int ngrp = 256 / dk;
-  const size_t smem = ((size_t)W * dk + (size_t)W * Tmax + (size_t)ngrp * W * dk) * sizeof(float);
+  const size_t smem = ((size_t)W * dk + (size_t)W * Tmax + (size_t)8 * W * dk) * sizeof(float);
   if (smem > 200 * 1024) { espb_set_error("dec_src_attn: beam*T too large for shared memory"); return ESPB_ERR_ARG; }
   static size_t cur_max = 48 * 1024;
   if (smem > cur_max) {
@@ -494,7 +561,7 @@ int espb_ctc_score_cands_f32(const float* logp, int U, int Tmax, int V, const in
                              const float* s_prev, const int* last_tok, int out_len, const int* cand, int P, float* part, float* psi, int* valid,
                              cudaStream_t stream) {
   const int n = U * W, tot = n * (P + 1);
-  ctc_score_cands_kernel<<<(tot + 127) / 128, 128, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, s_prev, last_tok, out_len, cand, P,
+  ctc_score_cands_kernel<<<(tot + 7) / 8, 256, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, s_prev, last_tok, out_len, cand, P,
                                                                 part, psi, valid);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
@@ -535,7 +602,7 @@ int espb_ctc_advance_f32(const float* logp, int U, int Tmax, int V, const int* l
                          const int* parent, const int* par_last_tok, const int* new_tok, const int* new_active, int out_len, float* r_new,
                          float* s_new, cudaStream_t stream) {
   const int n = U * W;
-  ctc_advance_kernel<<<(n + 31) / 32, 32, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, parent, par_last_tok, new_tok, new_active,
+  ctc_advance_kernel<<<(n + 3) / 4, 128, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, parent, par_last_tok, new_tok, new_active,
                                                        out_len, r_new, s_new);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
