@@ -107,7 +107,7 @@ __device__ __forceinline__ float epi_value(const EpiArgs& e, float acc, long lon
 // ------------------------------------------------------------------ tensor-core kernel
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym) {
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym, int axm, int aym) {
   constexpr int B_TILE_BYTES = BN * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -150,8 +150,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (p.a_mode == 0) {
           const int ko = (p.kob > 0) ? kb / p.kob : 0;
           const int ki = (p.kob > 0) ? kb % p.kob : kb;
-          tma_load_5d(sa, &tmA, fb, ki * BK, m0, bx + ko, by, 0);
-          tma_load_5d(sa + A_TILE_BYTES, &tmA, fb, ki * BK, m0, bx + ko, by, 1);
+          tma_load_5d(sa, &tmA, fb, ki * BK, m0, bx * axm + ko, by * aym, 0);
+          tma_load_5d(sa + A_TILE_BYTES, &tmA, fb, ki * BK, m0, bx * axm + ko, by * aym, 1);
         } else {  // conv2: tap (kt,kf) of the 3x3/stride-2 window over the parity-split conv1 output
           const int tap = kb / cblk, c0 = (kb % cblk) * BK;
           const int kt = tap / 3, kf = tap % 3;
@@ -195,7 +195,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     EpiArgs e;
     const long long coff = (long long)by * p.sc_y + (long long)bx * p.sc_x;
     e.C = p.C + coff; e.c_plane = p.c_plane; e.ldc = p.ldc; e.split_out = p.split_out;
-    e.bias = p.bias; e.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
+    e.bias = p.bias ? p.bias + (long long)bx * p.sbias_x : nullptr; e.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
     e.ldr = p.ldr; e.alpha = p.alpha; e.act = p.act;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((coff & 3) == 0) && ((p.c_plane & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
@@ -297,7 +297,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
 
 template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
-gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym) {
+gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym, int axm, int aym) {
   constexpr int BH = BN / 2;                      // B rows staged by each CTA
   constexpr int B_TILE_BYTES = BH * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
@@ -350,8 +350,8 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if (p.a_mode == 0) {
           const int ko = (p.kob > 0) ? kb / p.kob : 0;
           const int ki = (p.kob > 0) ? kb % p.kob : kb;
-          tma_load_5d_2sm(sa, &tmA, fb, ki * BK, m0, bx + ko, by, 0);
-          tma_load_5d_2sm(sa + A_TILE_BYTES, &tmA, fb, ki * BK, m0, bx + ko, by, 1);
+          tma_load_5d_2sm(sa, &tmA, fb, ki * BK, m0, bx * axm + ko, by * aym, 0);
+          tma_load_5d_2sm(sa + A_TILE_BYTES, &tmA, fb, ki * BK, m0, bx * axm + ko, by * aym, 1);
         } else {
           const int tap = kb / cblk, c0 = (kb % cblk) * BK;
           const int kt = tap / 3, kf = tap % 3;
@@ -419,7 +419,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     EpiArgs ea;
     const long long coff = (long long)by * p.sc_y + (long long)bx * p.sc_x;
     ea.C = p.C + coff; ea.c_plane = p.c_plane; ea.ldc = p.ldc; ea.split_out = p.split_out;
-    ea.bias = p.bias; ea.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
+    ea.bias = p.bias ? p.bias + (long long)bx * p.sbias_x : nullptr; ea.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
     ea.ldr = p.ldr; ea.alpha = p.alpha; ea.act = p.act;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((coff & 3) == 0) && ((p.c_plane & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(EspbGemmDesc p) {
   }
   EpiArgs e;
   e.C = p.C + (long long)by * p.sc_y + (long long)bx * p.sc_x; e.c_plane = p.c_plane; e.ldc = p.ldc; e.split_out = p.split_out;
-  e.bias = p.bias; e.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
+  e.bias = p.bias ? p.bias + (long long)bx * p.sbias_x : nullptr; e.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
   e.ldr = p.ldr; e.alpha = p.alpha; e.act = p.act;
   for (int i = 0; i < 4; ++i) {
     const int row = m0 + ty * 4 + i;
@@ -584,7 +584,7 @@ int make_map(CUtensorMap* map, const float* base, const long long dims[5], const
 }
 
 template <int BN, int STAGES>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, cudaStream_t stream) {
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
   constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * BN * 128) + 1024 + 16 * STAGES + 16;
   static bool attr_set = false;
   if (!attr_set) {
@@ -595,13 +595,13 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc
     attr_set = true;
   }
   dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.nbx * d.nby);
-  gemm_tf32x3_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym);
+  gemm_tf32x3_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
 
 template <int BN, int STAGES>
-int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, cudaStream_t stream) {
+int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
   constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * (BN / 2) * 128) + 1024 + 16 * STAGES + 64;
   static bool attr_set = false;
   if (!attr_set) {
@@ -612,7 +612,7 @@ int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDes
     attr_set = true;
   }
   dim3 grid(2 * ((d.M + 255) / 256), (d.N + BN - 1) / BN, d.nbx * d.nby);
-  gemm_tf32x3_2cta_kernel<BN, STAGES><<<grid, V2_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym);
+  gemm_tf32x3_2cta_kernel<BN, STAGES><<<grid, V2_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
@@ -623,10 +623,13 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
   if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.nbx <= 0 || d.nby <= 0) { espb_set_error("gemm: bad shape"); return ESPB_ERR_ARG; }
   CUtensorMap tmA, tmB;
   int rc;
+  int axm = 1, aym = 1;
   if (d.a_mode == 0) {
     long long n_outer = 1, k_inner = d.K;
     if (d.kob > 0) { k_inner = (long long)d.kob * BK; n_outer = (d.K + k_inner - 1) / k_inner; }
-    long long dims[5] = {k_inner, d.M, d.nbx + n_outer - 1, d.nby, 2};
+    axm = (d.sa_x != 0 && d.nbx > 1) ? 1 : 0;   // operand shared across a batch dim -> coordinate 0
+    aym = (d.sa_y != 0 && d.nby > 1) ? 1 : 0;
+    long long dims[5] = {k_inner, d.M, (axm ? d.nbx : 1) + n_outer - 1, aym ? d.nby : 1, 2};
     long long str[4] = {d.lda, d.sa_x, d.sa_y, d.a_plane};
     rc = make_map(&tmA, d.A, dims, str, BM);
   } else {
@@ -646,8 +649,8 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
     long long str[4] = {d.ldb, d.sb_x, d.sb_y, d.b_plane};
     rc = make_map(&tmB, d.B, dims, str, bn / 2);
     if (rc != ESPB_OK) return rc;
-    if (bn == 256) return launch_tc2<256, 3>(tmA, tmB, d, bxm, bym, stream);
-    return launch_tc2<128, 4>(tmA, tmB, d, bxm, bym, stream);
+    if (bn == 256) return launch_tc2<256, 3>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    return launch_tc2<128, 4>(tmA, tmB, d, bxm, bym, axm, aym, stream);
   }
   int bn;
   if (d.N <= 64) bn = 64;
@@ -661,9 +664,9 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
     rc = make_map(&tmB, d.B, dims, str, bn);
     if (rc != ESPB_OK) return rc;
   }
-  if (bn == 256) return launch_tc<256, 2>(tmA, tmB, d, bxm, bym, stream);
-  if (bn == 128) return launch_tc<128, 3>(tmA, tmB, d, bxm, bym, stream);
-  return launch_tc<64, 4>(tmA, tmB, d, bxm, bym, stream);
+  if (bn == 256) return launch_tc<256, 2>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+  if (bn == 128) return launch_tc<128, 3>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+  return launch_tc<64, 4>(tmA, tmB, d, bxm, bym, axm, aym, stream);
 }
 
 int espb_gemm_simt_launch(const EspbGemmDesc& d, cudaStream_t stream) {

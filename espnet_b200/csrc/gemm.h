@@ -20,6 +20,7 @@ struct EspbGemmDesc {
   float* C; long long c_plane, ldc, sc_x, sc_y;
   int split_out;        // 1: write hi/lo planes (c_plane apart); 0: plain fp32
   const float* bias;    // [N] or null
+  long long sbias_x;    // bias offset per batch-x index (heads as batch: bias + bx*sbias_x)
   const float* R; long long ldr, sr_x, sr_y;            // residual (may alias C) or null
   float alpha;          // out = R + alpha * act(acc + bias)   (R absent: alpha * act(...))
   int act;              // espb::ACT_*

@@ -107,43 +107,54 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------- cross-attention of W queries per utterance over the encoder memory
-// q [n][D]; memory K/V: kv + (u*Tmax + t)*kv_ld + k_off / v_off + h*dk.  One block per (utterance, head).
-__global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, long long kv_ld, int k_off,
-                                                           int v_off, int Tmax, const int* __restrict__ lens, int W, int D, int H,
+// q [n][D]; memory K / V blocks are contiguous per (utterance, head): kmem/vmem + ((u*H + h)*Tmax + t)*dk + d  (written once per
+// utterance by the K/V projection GEMMs and shared by the whole beam).  One block per (utterance, head): the K and V blocks are
+// streamed exactly once with coalesced 128-bit loads (LPR lanes per row, several rows per warp instruction, UN instructions in flight).
+template <int UN>
+__global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restrict__ q, const float* __restrict__ kmem, const float* __restrict__ vmem,
+                                                           int Tmax, const int* __restrict__ lens, int W, int D, int H, int lpr /* pow2 >= dk/4 */,
                                                            float* __restrict__ ctx, long long ctx_plane) {
-  extern __shared__ float sm[];  // q [W][dk] | scores [W][Tmax] | red [nwarp][W][dk]
+  extern __shared__ float sm[];  // q [W][dk] | scores [W][Tmax] (reused for the cross-warp PV reduction)
   const int u = blockIdx.x / H, h = blockIdx.x % H, dk = D / H;
   const int T = lens[u];
   float* qs = sm;
   float* sc = qs + W * dk;
-  float* red = sc + (long long)W * Tmax;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int i = threadIdx.x; i < W * dk; i += blockDim.x) qs[i] = q[((long long)(u * W + i / dk)) * D + h * dk + (i % dk)];
   __syncthreads();
+  const int rpw = 32 / lpr;                 // rows per warp instruction
+  const int rsub = lane / lpr, c4 = lane % lpr;   // row within the group, float4 column
+  const bool col_ok = c4 * 4 < dk;
   const float rs = sqrtf((float)dk);
-  const float* kbase = kv + (long long)u * Tmax * kv_ld + k_off + h * dk;
-  const float* vbase = kv + (long long)u * Tmax * kv_ld + v_off + h * dk;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const float* kr = kbase + (long long)t * kv_ld;
-    float a[16];
+  const float4* kb = reinterpret_cast<const float4*>(kmem + ((long long)(u * H + h) * Tmax) * dk);
+  const float4* vb = reinterpret_cast<const float4*>(vmem + ((long long)(u * H + h) * Tmax) * dk);
+  const int dk4 = dk / 4;
+  float4 qf[16];
 #pragma unroll
-    for (int w = 0; w < 16; ++w) a[w] = 0.f;
-    for (int d0 = 0; d0 < dk; d0 += 4) {
-      const float4 k4 = *reinterpret_cast<const float4*>(kr + d0);
+  for (int w = 0; w < 16; ++w) qf[w] = (w < W && col_ok) ? *reinterpret_cast<const float4*>(qs + w * dk + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // ---- scores[w][t] = q_w . k_t / sqrt(dk)
+  for (int t0 = warp * rpw * UN; t0 < T; t0 += nwarp * rpw * UN) {
+    float4 kv[UN];
+#pragma unroll
+    for (int uu = 0; uu < UN; ++uu) {
+      const int t = t0 + uu * rpw + rsub;
+      kv[uu] = (t < T && col_ok) ? __ldg(kb + (long long)t * dk4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int uu = 0; uu < UN; ++uu) {
+      const int t = t0 + uu * rpw + rsub;
 #pragma unroll
       for (int w = 0; w < 16; ++w) {
         if (w < W) {
-          const float* qw = qs + w * dk + d0;
-          a[w] = fmaf(qw[0], k4.x, a[w]); a[w] = fmaf(qw[1], k4.y, a[w]);
-          a[w] = fmaf(qw[2], k4.z, a[w]); a[w] = fmaf(qw[3], k4.w, a[w]);
+          float a = qf[w].x * kv[uu].x + qf[w].y * kv[uu].y + qf[w].z * kv[uu].z + qf[w].w * kv[uu].w;
+          for (int o = lpr >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          if (c4 == 0 && t < T) sc[w * Tmax + t] = a / rs;
         }
       }
     }
-#pragma unroll
-    for (int w = 0; w < 16; ++w) if (w < W) sc[w * Tmax + t] = a[w] / rs;
   }
   __syncthreads();
-  // softmax per slot: one warp per slot (round-robin)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  // ---- softmax over t per slot (no memory mask: batch_score passes none, transformer_decoder.py:294-303)
   for (int w = warp; w < W; w += nwarp) {
     float* r = sc + w * Tmax;
     float mx = -INFINITY;
@@ -155,41 +166,51 @@ __global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restri
     for (int t = lane; t < T; t += 32) r[t] = r[t] / sum;
   }
   __syncthreads();
-  // ctx[w][d] = sum_t p[w][t] * V[t][d]: warps split t, lanes split d (coalesced V rows), 8 rows in flight per warp
-  {
-    constexpr int UN = 8;
-    const int nd = (dk + 31) / 32;               // d values per lane (dk <= 256 -> <= 8); common case dk=64 -> 2
-    for (int dd = 0; dd < nd; ++dd) {
-      const int d = lane + 32 * dd;
-      float acc[16];
+  // ---- ctx[w][d] = sum_t p[w][t] * v[t][d]
+  float4 acc[16];
 #pragma unroll
-      for (int w = 0; w < 16; ++w) acc[w] = 0.f;
-      for (int t0 = warp * UN; t0 < T; t0 += nwarp * UN) {
-        float vv[UN];
+  for (int w = 0; w < 16; ++w) acc[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t0 = warp * rpw * UN; t0 < T; t0 += nwarp * rpw * UN) {
+    float4 vv[UN];
 #pragma unroll
-        for (int uu = 0; uu < UN; ++uu) {
-          const int t = t0 + uu;
-          vv[uu] = (t < T && d < dk) ? vbase[(long long)t * kv_ld + d] : 0.f;
+    for (int uu = 0; uu < UN; ++uu) {
+      const int t = t0 + uu * rpw + rsub;
+      vv[uu] = (t < T && col_ok) ? __ldg(vb + (long long)t * dk4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int uu = 0; uu < UN; ++uu) {
+      const int t = min(t0 + uu * rpw + rsub, T - 1);   // rows beyond T carry v = 0
+#pragma unroll
+      for (int w = 0; w < 16; ++w) {
+        if (w < W) {
+          const float pw = sc[w * Tmax + t];
+          acc[w].x = fmaf(pw, vv[uu].x, acc[w].x); acc[w].y = fmaf(pw, vv[uu].y, acc[w].y);
+          acc[w].z = fmaf(pw, vv[uu].z, acc[w].z); acc[w].w = fmaf(pw, vv[uu].w, acc[w].w);
         }
-#pragma unroll
-        for (int uu = 0; uu < UN; ++uu) {
-          const int t = min(t0 + uu, T - 1);
-#pragma unroll
-          for (int w = 0; w < 16; ++w)
-            if (w < W) acc[w] = fmaf(sc[w * Tmax + t], vv[uu], acc[w]);
-        }
-      }
-      if (d < dk) {
-#pragma unroll
-        for (int w = 0; w < 16; ++w)
-          if (w < W) red[((long long)warp * W + w) * dk + d] = acc[w];
       }
     }
+  }
+  // reduce over the rpw row groups of the warp (lanes with equal c4), then across warps through smem
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    if (w < W) {
+      for (int o = lpr; o < 32; o <<= 1) {
+        acc[w].x += __shfl_xor_sync(0xffffffffu, acc[w].x, o); acc[w].y += __shfl_xor_sync(0xffffffffu, acc[w].y, o);
+        acc[w].z += __shfl_xor_sync(0xffffffffu, acc[w].z, o); acc[w].w += __shfl_xor_sync(0xffffffffu, acc[w].w, o);
+      }
+    }
+  }
+  __syncthreads();   // probabilities are dead: reuse the score area as red[nwarp][W][dk]
+  float* red = sc;
+  if (rsub == 0 && col_ok) {
+#pragma unroll
+    for (int w = 0; w < 16; ++w)
+      if (w < W) *reinterpret_cast<float4*>(red + ((long long)warp * W + w) * dk + c4 * 4) = acc[w];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < W * dk; i += blockDim.x) {
     float a = 0.f;
-    for (int gg = 0; gg < nwarp; ++gg) a += red[(long long)gg * W * dk + i];
+    for (int g = 0; g < nwarp; ++g) a += red[(long long)g * W * dk + i];
     store_split(ctx + ((long long)(u * W + i / dk)) * D + h * dk + (i % dk), ctx_plane, a);
   }
 }
@@ -464,7 +485,7 @@ __global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restric
   const int c = new_tok[s];
   if (!new_active[s] || c == eos || c == blank) {   // ended / inactive hypotheses never use their state again
     for (int t = lane; t < Tmax; t += 32) ro[t] = make_float2(LOGZERO, LOGZERO);
-    if (lane == 0) s_new[s] = 0.f;
+    if (lane == 0) s_new[s] = (new_active[s] && c == blank) ? LOGZERO : 0.f;   // log_psi[blank] = logzero (ctc_prefix_score.py:187-189)
     return;
   }
   const int p = parent[s], T = lens[u];
@@ -524,20 +545,23 @@ int espb_dec_self_attn_f32(const float* qkv, float* kc, float* vc, const int* an
   return ESPB_OK;
 }
 
-int espb_dec_src_attn_f32(const float* q, const float* kv, long long kv_ld, int k_off, int v_off, int U, int Tmax, const int* lens, int W, int D,
-                          int H, float* ctx, long long ctx_plane, cudaStream_t stream) {
+int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, int U, int Tmax, const int* lens, int W, int D, int H, float* ctx,
+                          long long ctx_plane, cudaStream_t stream) {
   const int dk = D / H;
-  if (W > 16 || dk > 256 || (dk & 3)) { espb_set_error("dec_src_attn: needs beam <= 16 and d_k a multiple of 4, <= 256"); return ESPB_ERR_ARG; }
-  const size_t smem = ((size_t)W * dk + (size_t)W * Tmax + (size_t)8 * W * dk) * sizeof(float);
+  if (W > 16 || dk > 128 || (dk & 3)) { espb_set_error("dec_src_attn: needs beam <= 16 and d_k a multiple of 4, <= 128"); return ESPB_ERR_ARG; }
+  int lpr = 1;
+  while (lpr * 4 < dk) lpr <<= 1;
+  const size_t red = (size_t)8 * W * dk, scs = (size_t)W * Tmax;
+  const size_t smem = ((size_t)W * dk + (scs > red ? scs : red)) * sizeof(float);
   if (smem > 200 * 1024) { espb_set_error("dec_src_attn: beam*T too large for shared memory"); return ESPB_ERR_ARG; }
   static size_t cur_max = 48 * 1024;
   if (smem > cur_max) {
-    if (cudaFuncSetAttribute(dec_src_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
+    if (cudaFuncSetAttribute(dec_src_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
       espb_set_error("dec_src_attn: cannot raise dynamic shared memory"); return ESPB_ERR_CUDA;
     }
     cur_max = 200 * 1024;
   }
-  dec_src_attn_kernel<<<U * H, 256, smem, stream>>>(q, kv, kv_ld, k_off, v_off, Tmax, lens, W, D, H, ctx, ctx_plane);
+  dec_src_attn_kernel<4><<<U * H, 256, smem, stream>>>(q, kmem, vmem, Tmax, lens, W, D, H, lpr, ctx, ctx_plane);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

@@ -118,12 +118,18 @@ class TransformerDecoder(torch.nn.Module):
     # ---------------------------------------------------------------- device-side incremental scorer
     @torch.no_grad()
     def init_memory(self, enc_split, U, Tmax, lens32, n_slots, max_len):
-        """Project the encoder memory once: kv [U*Tmax][L*2D] (k_l | v_l per layer); allocate the self-attention cache."""
+        """Project the encoder memory once per utterance (shared by the beam); allocate the self-attention cache."""
         pk = self._packed or self._pack()
-        L, D = self.num_blocks, self.d
-        kv = self._buf("kv", (U * Tmax, L * 2 * D))
-        linear(enc_split, pk["kv_w"], kv, bias=pk["kv_b"])
-        st = dict(kv=kv, U=U, Tmax=Tmax, lens32=lens32, n=n_slots, max_len=max_len,
+        L, D, H = self.num_blocks, self.d, self.heads
+        dk = D // H
+        # kvmem[l][0|1][u][h][t][dk]: one contiguous block per (layer, k/v, utterance, head) -> the per-step cross-attention streams it
+        kvmem = self._buf("kvmem", (L, 2, U, H, Tmax, dk), zero=True)
+        for l in range(L):
+            for j in range(2):   # heads as batch-x (weight rows / bias / output block per head), utterances as batch-y
+                ops.gemm(Tmax, dk, D, enc_split, U * Tmax * D, D, pk["kv_w"], L * 2 * D * D, D, kvmem, dk, bias=pk["kv_b"],
+                         nbx=H, nby=U, sa=(0, Tmax * D), sb=(dk * D, 0), sc=(Tmax * dk, H * Tmax * dk), b_off=(l * 2 + j) * D * D,
+                         c_off=(l * 2 + j) * U * H * Tmax * dk, sbias_x=dk, bias_off=(l * 2 + j) * D)
+        st = dict(kvmem=kvmem, U=U, Tmax=Tmax, lens32=lens32, n=n_slots, max_len=max_len,
                   kc=self._buf("kc", (L, max_len, n_slots, D)), vc=self._buf("vc", (L, max_len, n_slots, D)),
                   pe=self._pe(max_len))
         return st
@@ -157,7 +163,7 @@ class TransformerDecoder(torch.nn.Module):
             linear(ctx, w["so_w"], x, bias=w["so_b"], residual=x)
             layernorm(x, *w["n2"], LN_EPS, out_split=xn)
             linear(xn, w["cq_w"], q, bias=w["cq_b"])
-            call("espb_dec_src_attn_f32", ptr(q), ptr(st["kv"]), L * 2 * D, li * 2 * D, li * 2 * D + D, st["U"], st["Tmax"],
+            call("espb_dec_src_attn_f32", ptr(q), ptr(st["kvmem"][li, 0]), ptr(st["kvmem"][li, 1]), st["U"], st["Tmax"],
                  ptr(st["lens32"]), W, D, H, ptr(ctx), n * D)
             _count()
             linear(ctx, w["co_w"], x, bias=w["co_b"], residual=x)

@@ -25,7 +25,7 @@ class GemmDesc(Structure):
         ("A", c_void_p), ("a_plane", c_longlong), ("lda", c_longlong), ("sa_x", c_longlong), ("sa_y", c_longlong),
         ("B", c_void_p), ("b_plane", c_longlong), ("ldb", c_longlong), ("sb_x", c_longlong), ("sb_y", c_longlong),
         ("C", c_void_p), ("c_plane", c_longlong), ("ldc", c_longlong), ("sc_x", c_longlong), ("sc_y", c_longlong),
-        ("split_out", c_int), ("bias", c_void_p),
+        ("split_out", c_int), ("bias", c_void_p), ("sbias_x", c_longlong),
         ("R", c_void_p), ("ldr", c_longlong), ("sr_x", c_longlong), ("sr_y", c_longlong),
         ("alpha", c_float), ("act", c_int), ("cv_t1h", c_int), ("cv_f1h", c_int), ("cv_cin", c_int),
     ]
@@ -52,7 +52,7 @@ _SIGS = {
     "espb_ctc_collapse_i32": [P, I, I, P, I, P, P, P],
     "espb_dec_embed_f32": [P, P, P, I, I, I, F, P, P],
     "espb_dec_self_attn_f32": [P, P, P, P, I, I, I, I, I, P, L, P],
-    "espb_dec_src_attn_f32": [P, P, L, I, I, I, I, P, I, I, I, P, L, P],
+    "espb_dec_src_attn_f32": [P, P, P, I, I, P, I, I, I, P, L, P],
     "espb_rows_topk_f32": [P, L, L, I, F, I, P, P, P],
     "espb_ctc_init_state_f32": [P, I, I, I, P, I, I, P, P, P],
     "espb_ctc_score_cands_f32": [P, I, I, I, P, I, I, I, P, P, P, I, P, I, P, P, P, P],

@@ -48,7 +48,7 @@ def split_from(x):
 
 def gemm(M, N, K, A, a_plane, lda, B, b_plane, ldb, C, ldc, *, c_plane=0, split_out=False, bias=None, R=None, ldr=0,
          alpha=1.0, act=ACT_NONE, nbx=1, nby=1, sa=(0, 0), sb=(0, 0), sc=(0, 0), sr=(0, 0), kob=0, a_mode=0, conv=(0, 0, 0),
-         a_off=0, b_off=0, c_off=0, r_off=0, force=None):
+         a_off=0, b_off=0, c_off=0, r_off=0, sbias_x=0, bias_off=0, force=None):
     """Raw strided GEMM launch; A/B/C/R are tensors (base pointers), *_off element offsets."""
     d = GemmDesc()
     d.M, d.N, d.K, d.nbx, d.nby, d.a_mode, d.kob = M, N, K, nbx, nby, a_mode, kob
@@ -59,7 +59,8 @@ def gemm(M, N, K, A, a_plane, lda, B, b_plane, ldb, C, ldc, *, c_plane=0, split_
     d.C = C.data_ptr() + 4 * c_off
     d.c_plane, d.ldc, d.sc_x, d.sc_y = c_plane, ldc, sc[0], sc[1]
     d.split_out = 1 if split_out else 0
-    d.bias = bias.data_ptr() if bias is not None else None
+    d.bias = (bias.data_ptr() + 4 * bias_off) if bias is not None else None
+    d.sbias_x = sbias_x
     d.R = (R.data_ptr() + 4 * r_off) if R is not None else None
     d.ldr, d.sr_x, d.sr_y = ldr, sr[0], sr[1]
     d.alpha, d.act = float(alpha), act

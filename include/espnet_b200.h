@@ -44,7 +44,7 @@ typedef struct EspbGemmDesc {
   const float* B; long long b_plane, ldb, sb_x, sb_y;
   float* C; long long c_plane, ldc, sc_x, sc_y;
   int split_out;
-  const float* bias;
+  const float* bias; long long sbias_x;   /* bias + bx*sbias_x */
   const float* R; long long ldr, sr_x, sr_y;
   float alpha;
   int act;
@@ -100,8 +100,9 @@ int espb_ctc_collapse_i32(const int* argmax, int B, int Tmax, const int* lens, i
 int espb_dec_embed_f32(const int* last_tok, const float* emb, const float* pe, int pos, int n, int D, float scale, float* x, cudaStream_t stream);
 int espb_dec_self_attn_f32(const float* qkv, float* kc, float* vc, const int* anc, int anc_ld, int n, int D, int H, int pos, float* ctx,
                            long long ctx_plane, cudaStream_t stream);
-int espb_dec_src_attn_f32(const float* q, const float* kv, long long kv_ld, int k_off, int v_off, int U, int Tmax, const int* lens, int W,
-                          int D, int H, float* ctx, long long ctx_plane, cudaStream_t stream);
+/* kmem / vmem: [U][H][Tmax][dk] blocks of one decoder layer (projected once per utterance). */
+int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, int U, int Tmax, const int* lens, int W, int D, int H, float* ctx,
+                          long long ctx_plane, cudaStream_t stream);
 
 /* ---- Beam search (batch_beam_search.py:253-423, beam_search.py:385-498, e2e_asr_common.py:14-44) -----------------------
  * rows_topk: torch.topk(dim=-1) of x*scale (pre-beam batch_beam_search.py:293-302 and per-row beam candidates). */
