@@ -111,10 +111,10 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
 // utterance by the K/V projection GEMMs and shared by the whole beam).  One block per (utterance, head): the K and V blocks are
 // streamed exactly once with coalesced 128-bit loads (LPR lanes per row, several rows per warp instruction, UN instructions in flight).
 template <int UN>
-__global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restrict__ q, const float* __restrict__ kmem, const float* __restrict__ vmem,
+__global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __restrict__ q, const float* __restrict__ kmem, const float* __restrict__ vmem,
                                                            int Tmax, const int* __restrict__ lens, int W, int D, int H, int lpr /* pow2 >= dk/4 */,
                                                            float* __restrict__ ctx, long long ctx_plane) {
-  extern __shared__ float sm[];  // q [W][dk] | scores [W][Tmax] (reused for the cross-warp PV reduction)
+  extern __shared__ float sm[];  // q [W][dk] | scores [W][Tmax] (reused for the cross-warp PV reduction) | K tile [128][dk+4]
   const int u = blockIdx.x / H, h = blockIdx.x % H, dk = D / H;
   const int T = lens[u];
   float* qs = sm;
@@ -129,28 +129,39 @@ __global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restri
   const float4* kb = reinterpret_cast<const float4*>(kmem + ((long long)(u * H + h) * Tmax) * dk);
   const float4* vb = reinterpret_cast<const float4*>(vmem + ((long long)(u * H + h) * Tmax) * dk);
   const int dk4 = dk / 4;
-  float4 qf[16];
-#pragma unroll
-  for (int w = 0; w < 16; ++w) qf[w] = (w < W && col_ok) ? *reinterpret_cast<const float4*>(qs + w * dk + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  // ---- scores[w][t] = q_w . k_t / sqrt(dk)
-  for (int t0 = warp * rpw * UN; t0 < T; t0 += nwarp * rpw * UN) {
-    float4 kv[UN];
-#pragma unroll
-    for (int uu = 0; uu < UN; ++uu) {
-      const int t = t0 + uu * rpw + rsub;
-      kv[uu] = (t < T && col_ok) ? __ldg(kb + (long long)t * dk4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int uu = 0; uu < UN; ++uu) {
-      const int t = t0 + uu * rpw + rsub;
-#pragma unroll
-      for (int w = 0; w < 16; ++w) {
-        if (w < W) {
-          float a = qf[w].x * kv[uu].x + qf[w].y * kv[uu].y + qf[w].z * kv[uu].z + qf[w].w * kv[uu].w;
-          for (int o = lpr >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-          if (c4 == 0 && t < T) sc[w * Tmax + t] = a / rs;
-        }
+  // ---- scores[w][t] = q_w . k_t / sqrt(dk): K tiles of 128 rows are staged in smem with coalesced 128-bit loads, then each thread
+  // owns one row (held in registers) and half of the beam slots: in-lane dot products, no shuffles.
+  {
+    float* kt = sc + (long long)W * Tmax;            // [128][dk + 4]
+    const int kst = dk + 4;
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int w_lo = half * ((W + 1) / 2), w_hi = min(W, w_lo + (W + 1) / 2);
+    for (int tb = 0; tb < T; tb += 128) {
+      const int rows = min(128, T - tb);
+      for (int i = threadIdx.x; i < rows * dk4; i += blockDim.x) {
+        const int rr = i / dk4, cc = i % dk4;
+        *reinterpret_cast<float4*>(kt + rr * kst + cc * 4) = __ldg(kb + (long long)(tb + rr) * dk4 + cc);
       }
+      __syncthreads();
+      if (r < rows) {
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 0.f;
+        for (int d0 = 0; d0 < dk; d0 += 4) {
+          const float4 k4 = *reinterpret_cast<const float4*>(kt + r * kst + d0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int w = w_lo + j;
+            if (w < w_hi) {
+              const float4 q4 = *reinterpret_cast<const float4*>(qs + w * dk + d0);
+              a[j] = fmaf(q4.x, k4.x, a[j]); a[j] = fmaf(q4.y, k4.y, a[j]); a[j] = fmaf(q4.z, k4.z, a[j]); a[j] = fmaf(q4.w, k4.w, a[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (w_lo + j < w_hi) sc[(w_lo + j) * Tmax + tb + r] = a[j] / rs;
+      }
+      __syncthreads();
     }
   }
   __syncthreads();
@@ -166,11 +177,14 @@ __global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restri
     for (int t = lane; t < T; t += 32) r[t] = r[t] / sum;
   }
   __syncthreads();
-  // ---- ctx[w][d] = sum_t p[w][t] * v[t][d]
-  float4 acc[16];
+  // ---- ctx[w][d] = sum_t p[w][t] * v[t][d]: the two halves of the block own the two halves of the beam slots (8 accumulators per
+  // lane); each half streams V with coalesced 128-bit loads, UN row groups in flight per warp.
+  const int hw = nwarp >> 1, hf = warp / hw, wh = warp % hw;
+  const int w_lo = hf * ((W + 1) / 2), w_hi = min(W, w_lo + (W + 1) / 2);
+  float4 acc[8];
 #pragma unroll
-  for (int w = 0; w < 16; ++w) acc[w] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t0 = warp * rpw * UN; t0 < T; t0 += nwarp * rpw * UN) {
+  for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t0 = wh * rpw * UN; t0 < T; t0 += hw * rpw * UN) {
     float4 vv[UN];
 #pragma unroll
     for (int uu = 0; uu < UN; ++uu) {
@@ -181,74 +195,83 @@ __global__ void __launch_bounds__(256) dec_src_attn_kernel(const float* __restri
     for (int uu = 0; uu < UN; ++uu) {
       const int t = min(t0 + uu * rpw + rsub, T - 1);   // rows beyond T carry v = 0
 #pragma unroll
-      for (int w = 0; w < 16; ++w) {
-        if (w < W) {
-          const float pw = sc[w * Tmax + t];
-          acc[w].x = fmaf(pw, vv[uu].x, acc[w].x); acc[w].y = fmaf(pw, vv[uu].y, acc[w].y);
-          acc[w].z = fmaf(pw, vv[uu].z, acc[w].z); acc[w].w = fmaf(pw, vv[uu].w, acc[w].w);
+      for (int j = 0; j < 8; ++j) {
+        if (w_lo + j < w_hi) {
+          const float pw = sc[(w_lo + j) * Tmax + t];
+          acc[j].x = fmaf(pw, vv[uu].x, acc[j].x); acc[j].y = fmaf(pw, vv[uu].y, acc[j].y);
+          acc[j].z = fmaf(pw, vv[uu].z, acc[j].z); acc[j].w = fmaf(pw, vv[uu].w, acc[j].w);
         }
       }
     }
   }
-  // reduce over the rpw row groups of the warp (lanes with equal c4), then across warps through smem
+  // reduce over the rpw row groups of the warp (lanes with equal c4), then across the warps of the half through smem
 #pragma unroll
-  for (int w = 0; w < 16; ++w) {
-    if (w < W) {
+  for (int j = 0; j < 8; ++j) {
+    if (w_lo + j < w_hi) {
       for (int o = lpr; o < 32; o <<= 1) {
-        acc[w].x += __shfl_xor_sync(0xffffffffu, acc[w].x, o); acc[w].y += __shfl_xor_sync(0xffffffffu, acc[w].y, o);
-        acc[w].z += __shfl_xor_sync(0xffffffffu, acc[w].z, o); acc[w].w += __shfl_xor_sync(0xffffffffu, acc[w].w, o);
+        acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o); acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
+        acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o); acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
       }
     }
   }
-  __syncthreads();   // probabilities are dead: reuse the score area as red[nwarp][W][dk]
+  __syncthreads();   // probabilities are dead: reuse the score area as red[hw][W][dk]
   float* red = sc;
   if (rsub == 0 && col_ok) {
 #pragma unroll
-    for (int w = 0; w < 16; ++w)
-      if (w < W) *reinterpret_cast<float4*>(red + ((long long)warp * W + w) * dk + c4 * 4) = acc[w];
+    for (int j = 0; j < 8; ++j)
+      if (w_lo + j < w_hi) *reinterpret_cast<float4*>(red + ((long long)wh * W + w_lo + j) * dk + c4 * 4) = acc[j];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < W * dk; i += blockDim.x) {
     float a = 0.f;
-    for (int g = 0; g < nwarp; ++g) a += red[(long long)g * W * dk + i];
+    for (int g = 0; g < hw; ++g) a += red[(long long)g * W * dk + i];
     store_split(ctx + ((long long)(u * W + i / dk)) * D + h * dk + (i % dk), ctx_plane, a);
   }
 }
 
 // ---------------------------------------------------------------- row-wise top-k (descending; ties -> lower index)
-// vals[r][k], ids[r][k] from x[r][0..V) * scale.  One block per row; k rounds of block arg-max.
+// vals[r][k], ids[r][k] from x[r][0..V) * scale.  One block per row; every thread keeps its V/256 values in registers and the
+// block runs k rounds of arg-max (winner knocked out by its owner).  V <= 256 * NV.
+template <int NV>
 __global__ void __launch_bounds__(256) rows_topk_kernel(const float* __restrict__ x, long long ld, int V, float scale, int k,
                                                         int* __restrict__ ids, float* __restrict__ vals) {
   __shared__ float bv[8]; __shared__ int bi[8];
-  __shared__ int chosen[64];
+  __shared__ int win_idx;
   const float* r = x + (long long)blockIdx.x * ld;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 256;
+    v[i] = (c < V) ? r[c] * scale : -INFINITY;
+  }
   for (int round = 0; round < k; ++round) {
     float best = -INFINITY; int idx = 0x7fffffff;
-    for (int i = threadIdx.x; i < V; i += blockDim.x) {
-      bool used = false;
-      for (int c = 0; c < round; ++c) used |= (chosen[c] == i);
-      if (used) continue;
-      float v = r[i] * scale;
-      if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = threadIdx.x + i * 256;
+      if (v[i] > best) { best = v[i]; idx = c; }   // ascending c within a thread: first maximum wins
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
       if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
     }
     if (lane == 0) { bv[warp] = best; bi[warp] = idx; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      float b = bv[0]; int id = bi[0];
-      for (int w = 1; w < (blockDim.x >> 5); ++w)
-        if (bv[w] > b || (bv[w] == b && bi[w] < id)) { b = bv[w]; id = bi[w]; }
-      chosen[round] = id;
+      float bb = bv[0]; int id = bi[0];
+      for (int w = 1; w < 8; ++w)
+        if (bv[w] > bb || (bv[w] == bb && bi[w] < id)) { bb = bv[w]; id = bi[w]; }
+      win_idx = id;
       ids[(long long)blockIdx.x * k + round] = id;
-      vals[(long long)blockIdx.x * k + round] = b;
+      vals[(long long)blockIdx.x * k + round] = bb;
     }
     __syncthreads();
+    const int wi = win_idx;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) if (threadIdx.x + i * 256 == wi) v[i] = -INFINITY;
   }
 }
 
@@ -260,38 +283,48 @@ __global__ void ctc_init_state_kernel(const float* __restrict__ logp, int Tmax, 
   if (s >= n) return;
   const int u = s / W;
   const int T = lens[u];
-  float* rr = r + (long long)s * Tmax * 2;
+  float4* rr = reinterpret_cast<float4*>(r) + (long long)s * Tmax;
   float c = 0.f;
   for (int t = 0; t < Tmax; ++t) {
     if (t < T) c += logp[((long long)u * Tmax + t) * V + blank];
-    rr[2 * t] = LOGZERO;
-    rr[2 * t + 1] = (t < T) ? c : LOGZERO;
+    const float rb = (t < T) ? c : LOGZERO;
+    rr[t] = make_float4(LOGZERO, rb, logaddexp(LOGZERO, rb), 0.f);
   }
   s_prev[s] = 0.f;
 }
 
 // log_phi[t] of the previous state: r_sum unless the candidate repeats the last label (ctc_prefix_score.py:135-144).
-__device__ __forceinline__ float ctc_phi(const float* __restrict__ rp, int t, bool same) {
-  const float p0 = rp[2 * t], p1 = rp[2 * t + 1];
-  return same ? p1 : logaddexp(p0, p1);
+// State layout: float4 per frame (r^n, r^b, r_sum = logaddexp(r^n, r^b), 0) so that scoring needs no transcendental for log_phi.
+__device__ __forceinline__ float ctc_phi(const float4* __restrict__ rp, int t, bool same) {
+  const float4 v = __ldg(rp + t);
+  return same ? v.y : v.z;
 }
 
 // log_psi of extending the prefix of a slot by token c (ctc_prefix_score.py:166-189).  It depends only on the PREVIOUS state:
 //   log_psi = logsumexp( {log_phi[t-1] + x[t,c]}_{t=start..T-1}, r[start-1,0] ),   r[start-1,0] = x[0,c] if the prefix is empty else logzero
 // so it is a reduction over t: one warp per (slot, candidate), lanes stride t.  Must be called by a full warp.
-__device__ __forceinline__ float ctc_log_psi_warp(const float* __restrict__ x, int V, int T, int blank, int eos, const float* __restrict__ rp, int c,
+__device__ __forceinline__ float ctc_log_psi_warp(const float* __restrict__ x, int V, int T, int blank, int eos, const float4* __restrict__ rp, int c,
                                                   int last, int out_len, int lane) {
-  if (c == eos) return logaddexp(rp[2 * (T - 1)], rp[2 * (T - 1) + 1]);   // (:184-185)
+  if (c == eos) return __ldg(rp + (T - 1)).z;                             // (:184-185) r_sum[T-1]
   if (c == blank) return LOGZERO;                                          // (:187-189)
   const int start = max(out_len, 1);
   const bool same = (c == last);
-  const float r0 = (out_len == 0) ? x[c] : LOGZERO;
-  float m = -INFINITY;
-  for (int t = start + lane; t < T; t += 32) m = fmaxf(m, ctc_phi(rp, t - 1, same) + x[(long long)t * V + c]);
-  m = fmaxf(espb::warp_max(m), r0);
-  float ssum = 0.f;
-  for (int t = start + lane; t < T; t += 32) ssum += expf(ctc_phi(rp, t - 1, same) + x[(long long)t * V + c] - m);
-  ssum = espb::warp_sum(ssum) + expf(r0 - m);
+  float m = -INFINITY, ssum = 0.f;   // per-lane streaming log-sum-exp, merged across the warp at the end
+  for (int t = start + lane; t < T; t += 32) {
+    const float e = ctc_phi(rp, t - 1, same) + __ldg(x + (long long)t * V + c);
+    if (e > m) { ssum = ssum * expf(m - e) + 1.f; m = e; } else { ssum += expf(e - m); }
+  }
+  if (lane == 0) {   // the r[start-1,0] term
+    const float r0 = (out_len == 0) ? x[c] : LOGZERO;
+    if (r0 > m) { ssum = ssum * expf(m - r0) + 1.f; m = r0; } else { ssum += expf(r0 - m); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, ssum, o);
+    const float nm = fmaxf(m, om);
+    ssum = (m == -INFINITY ? 0.f : ssum * expf(m - nm)) + (om == -INFINITY ? 0.f : os * expf(om - nm));
+    m = nm;
+  }
   return m + logf(ssum);
 }
 
@@ -309,7 +342,7 @@ __global__ void __launch_bounds__(256) ctc_score_cands_kernel(const float* __res
   const int c = (j < P) ? cand[(long long)s * P + j] : eos;
   int ok = 1;
   if (j == P) for (int q = 0; q < P; ++q) if (cand[(long long)s * P + q] == eos) ok = 0;
-  const float v = ctc_log_psi_warp(logp + (long long)u * Tmax * V, V, lens[u], blank, eos, r_prev + (long long)s * Tmax * 2, c, last_tok[s],
+  const float v = ctc_log_psi_warp(logp + (long long)u * Tmax * V, V, lens[u], blank, eos, reinterpret_cast<const float4*>(r_prev) + (long long)s * Tmax, c, last_tok[s],
                                    out_len, lane);
   if (lane == 0) { psi[idx] = v; part[idx] = v - s_prev[s]; valid[idx] = ok; }
 }
@@ -324,9 +357,9 @@ __global__ void __launch_bounds__(128) ctc_score_dense_kernel(const float* __res
   const int s = (int)(idx / V), c = (int)(idx % V);
   const int u = s / W, T = lens[u];
   const float* x = logp + (long long)u * Tmax * V;
-  const float* rp = r_prev + (long long)s * Tmax * 2;
+  const float4* rp = reinterpret_cast<const float4*>(r_prev) + (long long)s * Tmax;
   float v;
-  if (c == eos) v = logaddexp(rp[2 * (T - 1)], rp[2 * (T - 1) + 1]);
+  if (c == eos) v = __ldg(rp + (T - 1)).z;
   else if (c == blank) v = LOGZERO;
   else {
     const int start = max(out_len, 1);
@@ -481,22 +514,23 @@ __global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restric
   const int lane = threadIdx.x & 31;
   if (s >= n) return;
   const int u = s / W;
-  float2* ro = reinterpret_cast<float2*>(r_new + (long long)s * Tmax * 2);
+  float4* ro = reinterpret_cast<float4*>(r_new) + (long long)s * Tmax;
+  const float4 Z4 = make_float4(LOGZERO, LOGZERO, logaddexp(LOGZERO, LOGZERO), 0.f);
   const int c = new_tok[s];
   if (!new_active[s] || c == eos || c == blank) {   // ended / inactive hypotheses never use their state again
-    for (int t = lane; t < Tmax; t += 32) ro[t] = make_float2(LOGZERO, LOGZERO);
+    for (int t = lane; t < Tmax; t += 32) ro[t] = Z4;
     if (lane == 0) s_new[s] = (new_active[s] && c == blank) ? LOGZERO : 0.f;   // log_psi[blank] = logzero (ctc_prefix_score.py:187-189)
     return;
   }
   const int p = parent[s], T = lens[u];
   const float* x = logp + (long long)u * Tmax * V;
-  const float* rp = r_prev + (long long)p * Tmax * 2;
+  const float4* rp = reinterpret_cast<const float4*>(r_prev) + (long long)p * Tmax;
   const int last = par_last_tok[p];
   const bool same = (c == last);
   const int start = max(out_len, 1);
   float rn = (out_len == 0) ? x[c] : LOGZERO, rb = LOGZERO;   // r[start-1]
-  for (int t = lane; t < start - 1; t += 32) ro[t] = make_float2(LOGZERO, LOGZERO);
-  if (lane == 0) ro[start - 1] = make_float2(rn, rb);
+  for (int t = lane; t < start - 1; t += 32) ro[t] = Z4;
+  if (lane == 0) ro[start - 1] = make_float4(rn, rb, logaddexp(rn, rb), 0.f);
   for (int t0 = start; t0 < T; t0 += 32) {
     const int t = t0 + lane;
     float phi = LOGZERO, xc = 0.f, xb = 0.f;
@@ -510,9 +544,9 @@ __global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restric
       rn = nrn; rb = nrb;
       if (lane == i) { my_n = rn; my_b = rb; }
     }
-    if (t < T) ro[t] = make_float2(my_n, my_b);
+    if (t < T) ro[t] = make_float4(my_n, my_b, logaddexp(my_n, my_b), 0.f);
   }
-  for (int t = T + lane; t < Tmax; t += 32) ro[t] = make_float2(LOGZERO, LOGZERO);
+  for (int t = T + lane; t < Tmax; t += 32) ro[t] = Z4;
   const float psi = ctc_log_psi_warp(x, V, T, blank, eos, rp, c, last, out_len, lane);
   if (lane == 0) s_new[s] = psi;
 }
@@ -552,7 +586,7 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
   int lpr = 1;
   while (lpr * 4 < dk) lpr <<= 1;
   const size_t red = (size_t)8 * W * dk, scs = (size_t)W * Tmax;
-  const size_t smem = ((size_t)W * dk + (scs > red ? scs : red)) * sizeof(float);
+  const size_t smem = ((size_t)W * dk + (scs > red ? scs : red) + (size_t)128 * (dk + 4)) * sizeof(float);
   if (smem > 200 * 1024) { espb_set_error("dec_src_attn: beam*T too large for shared memory"); return ESPB_ERR_ARG; }
   static size_t cur_max = 48 * 1024;
   if (smem > cur_max) {
@@ -567,8 +601,11 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
 }
 
 int espb_rows_topk_f32(const float* x, long long rows, long long ld, int V, float scale, int k, int* ids, float* vals, cudaStream_t stream) {
-  if (k > 64 || k > V) { espb_set_error("rows_topk: k must be <= min(64, V)"); return ESPB_ERR_ARG; }
-  rows_topk_kernel<<<(unsigned)rows, 256, 0, stream>>>(x, ld, V, scale, k, ids, vals);
+  if (k > 64 || k > V || V > 256 * 128) { espb_set_error("rows_topk: k must be <= min(64, V) and V <= 32768"); return ESPB_ERR_ARG; }
+  if (V <= 256 * 4) rows_topk_kernel<4><<<(unsigned)rows, 256, 0, stream>>>(x, ld, V, scale, k, ids, vals);
+  else if (V <= 256 * 20) rows_topk_kernel<20><<<(unsigned)rows, 256, 0, stream>>>(x, ld, V, scale, k, ids, vals);
+  else if (V <= 256 * 40) rows_topk_kernel<40><<<(unsigned)rows, 256, 0, stream>>>(x, ld, V, scale, k, ids, vals);
+  else rows_topk_kernel<128><<<(unsigned)rows, 256, 0, stream>>>(x, ld, V, scale, k, ids, vals);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

@@ -108,7 +108,7 @@ class BatchBeamSearch(torch.nn.Module):
         logp_ctc = part = psi = valid = r = s_prev = None
         if use_ctc:
             logp_ctc = self.ctc.log_softmax(enc, enc_split)           # (U, Tmax, V), scorers/ctc.py:96-99
-            r = [f32(n, Tmax, 2), f32(n, Tmax, 2)]
+            r = [f32(n, Tmax, 4), f32(n, Tmax, 4)]   # per frame (r^n, r^b, r_sum, pad)
             s_prev = [f32(n), f32(n)]
             call("espb_ctc_init_state_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, W, ptr(r[0]), ptr(s_prev[0]))
             _count()
@@ -117,6 +117,12 @@ class BatchBeamSearch(torch.nn.Module):
             else:
                 part = f32(n, V)
         end_detect = 1 if maxlenratio == 0.0 else 0
+        # the CTC state update of step i is only consumed by the CTC scoring of step i+1 (after the next decoder pass): run it on a
+        # side stream so that its T-step sequential recursion overlaps the decoder
+        main = torch.cuda.current_stream()
+        side = self._side_stream(dev) if (use_ctc and use_dec) else None
+        ev_sel, ev_adv = torch.cuda.Event(), torch.cuda.Event()
+        adv_pending = False
         cur = 0
         steps_run = 0
         for i in range(cap):
@@ -124,6 +130,9 @@ class BatchBeamSearch(torch.nn.Module):
             logp_dec = None
             if use_dec:
                 logp_dec = self.decoder.step(dst, i, last_tok[cur], anc[cur], W)
+            if adv_pending:
+                main.wait_event(ev_adv)
+                adv_pending = False
             if mode == 1:
                 ops.rows_topk(logp_dec, self.w_dec, P, cand_ids, cand_val)
                 call("espb_ctc_score_cands_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
@@ -146,8 +155,17 @@ class BatchBeamSearch(torch.nn.Module):
                 call("espb_anc_update_i32", ptr(anc[cur]), ptr(anc[nxt]), cap + 1, ptr(parent), i, n)
                 _count()
             if use_ctc:
-                call("espb_ctc_advance_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(parent),
-                     ptr(last_tok[cur]), ptr(last_tok[nxt]), ptr(active[nxt]), i, ptr(r[nxt]), ptr(s_prev[nxt]))
+                if side is not None:
+                    ev_sel.record(main)
+                    with torch.cuda.stream(side):
+                        side.wait_event(ev_sel)
+                        call("espb_ctc_advance_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(parent),
+                             ptr(last_tok[cur]), ptr(last_tok[nxt]), ptr(active[nxt]), i, ptr(r[nxt]), ptr(s_prev[nxt]))
+                        ev_adv.record(side)
+                    adv_pending = True
+                else:
+                    call("espb_ctc_advance_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(parent),
+                         ptr(last_tok[cur]), ptr(last_tok[nxt]), ptr(active[nxt]), i, ptr(r[nxt]), ptr(s_prev[nxt]))
                 _count()
             cur = nxt
             steps_run = i + 1
@@ -156,7 +174,17 @@ class BatchBeamSearch(torch.nn.Module):
                 _count()
                 if int(n_active.item()) == 0:
                     break
+        if side is not None:
+            main.wait_stream(side)
         return self._collect(U, W, steps_run, maxlen, bp_parent, bp_token, e_count, e_step, e_slot, e_score, e_dec, e_ctc)
+
+    def _side_stream(self, dev):
+        key = str(dev)
+        if not hasattr(self, "_streams"):
+            self._streams = {}
+        if key not in self._streams:
+            self._streams[key] = torch.cuda.Stream(device=dev)
+        return self._streams[key]
 
     def _collect(self, U, W, steps, maxlen, bp_parent, bp_token, e_count, e_step, e_slot, e_score, e_dec, e_ctc):
         """Host post-processing: rebuild token sequences from back-pointers and sort (beam_search.py:452-459)."""

@@ -108,7 +108,7 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
  * rows_topk: torch.topk(dim=-1) of x*scale (pre-beam batch_beam_search.py:293-302 and per-row beam candidates). */
 int espb_rows_topk_f32(const float* x, long long rows, long long ld, int V, float scale, int k, int* ids, float* vals, cudaStream_t stream);
 /* CTCPrefixScoreTH (ctc_prefix_score.py:71-191) + CTCPrefixScorer.select_state (scorers/ctc.py:40-63):
- * r [n][Tmax][2] forward variables (r^n, r^b), s_prev [n] previous log_psi. */
+ * r [n][Tmax][4] forward variables per frame (r^n, r^b, r_sum = logaddexp(r^n, r^b), pad), s_prev [n] previous log_psi. */
 int espb_ctc_init_state_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int W, float* r, float* s_prev,
                             cudaStream_t stream);
 int espb_ctc_score_cands_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
