@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __res
   // ---- scores[w][t] = q_w . k_t / sqrt(dk): K tiles of 128 rows are staged in smem with coalesced 128-bit loads, then each thread
   // owns one row (held in registers) and half of the beam slots: in-lane dot products, no shuffles.
   {
-    float* kt = sc + (long long)W * Tmax;            // [128][dk + 4]
+    float* kt = sc + (((long long)W * Tmax + 3) & ~3LL);   // [128][dk + 4], 16-byte aligned
     const int kst = dk + 4;
     const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
     const int w_lo = half * ((W + 1) / 2), w_hi = min(W, w_lo + (W + 1) / 2);
@@ -585,7 +585,7 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
   if (W > 16 || dk > 128 || (dk & 3)) { espb_set_error("dec_src_attn: needs beam <= 16 and d_k a multiple of 4, <= 128"); return ESPB_ERR_ARG; }
   int lpr = 1;
   while (lpr * 4 < dk) lpr <<= 1;
-  const size_t red = (size_t)8 * W * dk, scs = (size_t)W * Tmax;
+  const size_t red = (size_t)8 * W * dk, scs = ((size_t)W * Tmax + 3) & ~(size_t)3;
   const size_t smem = ((size_t)W * dk + (scs > red ? scs : red) + (size_t)128 * (dk + 4)) * sizeof(float);
   if (smem > 200 * 1024) { espb_set_error("dec_src_attn: beam*T too large for shared memory"); return ESPB_ERR_ARG; }
   static size_t cur_max = 48 * 1024;
