@@ -21,8 +21,9 @@ __device__ __forceinline__ void store_split(float* p, long long plane, float v) 
 }
 
 // ---------------------------------------------------------------- decoder input: embed(last token)*sqrt(D) + PE[pos]
-__global__ void dec_embed_kernel(const int* __restrict__ last_tok, const float* __restrict__ emb, const float* __restrict__ pe, int pos, int D,
-                                 float scale, float* __restrict__ x) {
+__global__ void dec_embed_kernel(const int* __restrict__ last_tok, const float* __restrict__ emb, const float* __restrict__ pe, int pos,
+                                 const int* __restrict__ step_ptr, int D, float scale, float* __restrict__ x) {
+  if (step_ptr) pos += *step_ptr;
   const int s = blockIdx.x;
   const float* e = emb + (long long)last_tok[s] * D;
   const float* p = pe + (long long)pos * D;
@@ -35,13 +36,15 @@ __global__ void dec_embed_kernel(const int* __restrict__ last_tok, const float* 
 // that every K/V row is one coalesced read; 4 positions are in flight per iteration.
 __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc,
                                                             const int* __restrict__ anc, int anc_ld, int n, int D, int H, int pos,
-                                                            float* __restrict__ ctx, long long ctx_plane) {
-  extern __shared__ float sm[];  // per warp: (pos+1) scores
+                                                            const int* __restrict__ step_ptr, int sc_ld, float* __restrict__ ctx,
+                                                            long long ctx_plane) {
+  extern __shared__ float sm[];  // per warp: sc_ld >= pos+1 scores
+  if (step_ptr) pos += *step_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wid = blockIdx.x * (blockDim.x >> 5) + warp;
   if (wid >= n * H) return;
   const int s = wid / H, h = wid % H, dk = D / H;
-  float* sc = sm + warp * (pos + 1);
+  float* sc = sm + warp * sc_ld;
   const float* q = qkv + (long long)s * 3 * D + h * dk;
   float qr[4], kn[4], vn[4];
 #pragma unroll
@@ -332,8 +335,10 @@ __device__ __forceinline__ float ctc_log_psi_warp(const float* __restrict__ x, i
 // and psi[n][P+1]. Duplicate eos (eos already among the P) is flagged by valid[n][P+1] = 0.  One warp per (slot, candidate).
 __global__ void __launch_bounds__(256) ctc_score_cands_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank,
                                                               int eos, int W, int n, const float* __restrict__ r_prev, const float* __restrict__ s_prev,
-                                                              const int* __restrict__ last_tok, int out_len, const int* __restrict__ cand, int P,
-                                                              float* __restrict__ part, float* __restrict__ psi, int* __restrict__ valid) {
+                                                              const int* __restrict__ last_tok, int out_len, const int* __restrict__ step_ptr,
+                                                              const int* __restrict__ cand, int P, float* __restrict__ part,
+                                                              float* __restrict__ psi, int* __restrict__ valid) {
+  if (step_ptr) out_len += *step_ptr;
   const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (idx >= n * (P + 1)) return;
@@ -392,11 +397,13 @@ struct BeamState {
 // mode 1: joint             -- candidates j<P from the pre-beam + eos as candidate P; part/valid [n][P+1]
 //                              total = ((dec + penalty) + w_ctc*part) + score   (batch_beam_search.py:293-309)
 // mode 2: CTC only (dense)  -- cand_val[n][P] = w_ctc*part of cand_ids, part = dense [n][V]
-__global__ void __launch_bounds__(32) beam_select_kernel(BeamState st, int U, int W, int P, int V, int step, const int* __restrict__ maxlen,
+__global__ void __launch_bounds__(32) beam_select_kernel(BeamState st, int U, int W, int P, int V, int step, const int* __restrict__ step_ptr,
+                                                         const int* __restrict__ maxlen,
                                                          const int* __restrict__ minlen, int eos, float w_dec, float w_ctc, float penalty, int mode,
                                                          const int* __restrict__ cand_ids, const float* __restrict__ cand_val,
                                                          const float* __restrict__ logp_dec /* [n][V] or null */, const float* __restrict__ part,
                                                          const int* __restrict__ valid, int end_detect, int maxlen_cap) {
+  if (step_ptr) step += *step_ptr;
   const int u = blockIdx.x, lane = threadIdx.x;
   const int PC = (mode == 1) ? P + 1 : P;   // candidates per slot
   const int total = W * PC;
@@ -495,7 +502,9 @@ __global__ void __launch_bounds__(32) beam_select_kernel(BeamState st, int U, in
 }
 
 // After selection: rows of the ancestor table and CTC states follow their parents.
-__global__ void anc_update_kernel(const int* __restrict__ anc, int* __restrict__ n_anc, int anc_ld, const int* __restrict__ parent, int pos, int n) {
+__global__ void anc_update_kernel(const int* __restrict__ anc, int* __restrict__ n_anc, int anc_ld, const int* __restrict__ parent, int pos,
+                                  const int* __restrict__ step_ptr, int n) {
+  if (step_ptr) pos += *step_ptr;
   const int s = blockIdx.x;
   const int p = parent[s];
   for (int j = threadIdx.x; j < pos; j += blockDim.x) n_anc[(long long)s * anc_ld + j] = anc[(long long)p * anc_ld + j];
@@ -508,8 +517,9 @@ __global__ void anc_update_kernel(const int* __restrict__ anc, int* __restrict__
 __global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restrict__ logp, int Tmax, int V, const int* __restrict__ lens, int blank, int eos,
                                                           int W, int n, const float* __restrict__ r_prev, const int* __restrict__ parent,
                                                           const int* __restrict__ par_last_tok, const int* __restrict__ new_tok,
-                                                          const int* __restrict__ new_active, int out_len, float* __restrict__ r_new,
-                                                          float* __restrict__ s_new) {
+                                                          const int* __restrict__ new_active, int out_len, const int* __restrict__ step_ptr,
+                                                          float* __restrict__ r_new, float* __restrict__ s_new) {
+  if (step_ptr) out_len += *step_ptr;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (s >= n) return;
@@ -551,6 +561,8 @@ __global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restric
   if (lane == 0) s_new[s] = psi;
 }
 
+__global__ void step_inc_kernel(int* step) { *step += 1; }
+
 __global__ void count_active_kernel(const int* __restrict__ active, int n, int* __restrict__ out) {
   __shared__ float red[33];
   float c = 0.f;
@@ -563,18 +575,21 @@ __global__ void count_active_kernel(const int* __restrict__ active, int n, int* 
 
 extern "C" {
 
-int espb_dec_embed_f32(const int* last_tok, const float* emb, const float* pe, int pos, int n, int D, float scale, float* x, cudaStream_t stream) {
-  dec_embed_kernel<<<n, 128, 0, stream>>>(last_tok, emb, pe, pos, D, scale, x);
+int espb_dec_embed_f32(const int* last_tok, const float* emb, const float* pe, int pos, const int* step_ptr, int n, int D, float scale, float* x,
+                       cudaStream_t stream) {
+  dec_embed_kernel<<<n, 128, 0, stream>>>(last_tok, emb, pe, pos, step_ptr, D, scale, x);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
 
-int espb_dec_self_attn_f32(const float* qkv, float* kc, float* vc, const int* anc, int anc_ld, int n, int D, int H, int pos, float* ctx,
-                           long long ctx_plane, cudaStream_t stream) {
+int espb_dec_self_attn_f32(const float* qkv, float* kc, float* vc, const int* anc, int anc_ld, int n, int D, int H, int pos, const int* step_ptr,
+                           int max_pos, float* ctx, long long ctx_plane, cudaStream_t stream) {
   const int warps = 4;
-  const size_t smem = (size_t)warps * (pos + 1) * sizeof(float);
+  const int sc_ld = (step_ptr ? max_pos : pos) + 1;   // with a device-side step the score buffer is sized for the longest prefix
+  const size_t smem = (size_t)warps * sc_ld * sizeof(float);
   if (smem > 48 * 1024) { espb_set_error("dec_self_attn: prefix too long for the score buffer"); return ESPB_ERR_ARG; }
-  dec_self_attn_kernel<<<(n * H + warps - 1) / warps, warps * 32, smem, stream>>>(qkv, kc, vc, anc, anc_ld, n, D, H, pos, ctx, ctx_plane);
+  dec_self_attn_kernel<<<(n * H + warps - 1) / warps, warps * 32, smem, stream>>>(qkv, kc, vc, anc, anc_ld, n, D, H, pos, step_ptr, sc_ld, ctx,
+                                                                                  ctx_plane);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
@@ -619,11 +634,11 @@ int espb_ctc_init_state_f32(const float* logp, int U, int Tmax, int V, const int
 }
 
 int espb_ctc_score_cands_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
-                             const float* s_prev, const int* last_tok, int out_len, const int* cand, int P, float* part, float* psi, int* valid,
-                             cudaStream_t stream) {
+                             const float* s_prev, const int* last_tok, int out_len, const int* step_ptr, const int* cand, int P, float* part,
+                             float* psi, int* valid, cudaStream_t stream) {
   const int n = U * W, tot = n * (P + 1);
-  ctc_score_cands_kernel<<<(tot + 7) / 8, 256, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, s_prev, last_tok, out_len, cand, P,
-                                                                part, psi, valid);
+  ctc_score_cands_kernel<<<(tot + 7) / 8, 256, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, s_prev, last_tok, out_len, step_ptr, cand,
+                                                              P, part, psi, valid);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
@@ -640,31 +655,38 @@ int espb_ctc_score_dense_f32(const float* logp, int U, int Tmax, int V, const in
 int espb_beam_select(const float* score, const float* sc_dec, const float* sc_ctc, const int* active, float* n_score, float* n_sc_dec,
                      float* n_sc_ctc, int* n_active, int* n_last_tok, int* n_parent, int* bp_parent, int* bp_token, int* ended_count,
                      int* ended_step, int* ended_slot, float* ended_score, float* ended_dec, float* ended_ctc, int ended_cap, float* best_at_step,
-                     float* best_all, int* utt_done, int U, int W, int P, int V, int step, const int* maxlen, const int* minlen, int eos,
+                     float* best_all, int* utt_done, int U, int W, int P, int V, int step, const int* step_ptr, const int* maxlen,
+                     const int* minlen, int eos,
                      float w_dec, float w_ctc, float penalty, int mode, const int* cand_ids, const float* cand_val, const float* logp_dec,
                      const float* part, const int* valid, int end_detect, int maxlen_cap, cudaStream_t stream) {
   const int PC = (mode == 1) ? P + 1 : P;
   if (W * PC > 768 || W > 32 || mode < 0 || mode > 2) { espb_set_error("beam_select: beam * candidates > 768 or bad mode"); return ESPB_ERR_ARG; }
   BeamState st{score, sc_dec, sc_ctc, active, n_score, n_sc_dec, n_sc_ctc, n_active, n_last_tok, n_parent, bp_parent, bp_token,
                ended_count, ended_step, ended_slot, ended_score, ended_dec, ended_ctc, ended_cap, best_at_step, best_all, utt_done};
-  beam_select_kernel<<<U, 32, 0, stream>>>(st, U, W, P, V, step, maxlen, minlen, eos, w_dec, w_ctc, penalty, mode, cand_ids, cand_val, logp_dec,
+  beam_select_kernel<<<U, 32, 0, stream>>>(st, U, W, P, V, step, step_ptr, maxlen, minlen, eos, w_dec, w_ctc, penalty, mode, cand_ids, cand_val, logp_dec,
                                            part, valid, end_detect, maxlen_cap);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
 
-int espb_anc_update_i32(const int* anc, int* n_anc, int anc_ld, const int* parent, int pos, int n, cudaStream_t stream) {
-  anc_update_kernel<<<n, 64, 0, stream>>>(anc, n_anc, anc_ld, parent, pos, n);
+int espb_anc_update_i32(const int* anc, int* n_anc, int anc_ld, const int* parent, int pos, const int* step_ptr, int n, cudaStream_t stream) {
+  anc_update_kernel<<<n, 64, 0, stream>>>(anc, n_anc, anc_ld, parent, pos, step_ptr, n);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
 
 int espb_ctc_advance_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
-                         const int* parent, const int* par_last_tok, const int* new_tok, const int* new_active, int out_len, float* r_new,
-                         float* s_new, cudaStream_t stream) {
+                         const int* parent, const int* par_last_tok, const int* new_tok, const int* new_active, int out_len, const int* step_ptr,
+                         float* r_new, float* s_new, cudaStream_t stream) {
   const int n = U * W;
   ctc_advance_kernel<<<(n + 3) / 4, 128, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, parent, par_last_tok, new_tok, new_active,
-                                                       out_len, r_new, s_new);
+                                                       out_len, step_ptr, r_new, s_new);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_step_inc_i32(int* step, cudaStream_t stream) {
+  step_inc_kernel<<<1, 1, 0, stream>>>(step);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

@@ -30,18 +30,20 @@ class CTC(torch.nn.Module):
         return split_from(hs_pad.contiguous().float().view(-1, hs_pad.shape[-1]))
 
     @torch.no_grad()
-    def logits(self, hs_pad, hs_split=None):
-        """(B, T, D) -> (B, T, V) = ctc_lo(hs_pad)."""
+    def logits(self, hs_pad, hs_split=None, out=None):
+        """(B, T, D) -> (B, T, V) = ctc_lo(hs_pad); `out` optionally provides the (B*T, V) result buffer."""
         w, b = self._packed or self._pack()
         B, T, D = hs_pad.shape
         xs = self._split_input(hs_pad, hs_split)
-        out = torch.empty(B * T, self.odim, dtype=torch.float32, device=hs_pad.device)
+        if out is None:
+            out = torch.empty(B * T, self.odim, dtype=torch.float32, device=hs_pad.device)
+        out = out.view(B * T, self.odim)
         linear(xs, w, out, bias=b)
         return out.view(B, T, self.odim)
 
     @torch.no_grad()
-    def log_softmax(self, hs_pad, hs_split=None):
-        lg = self.logits(hs_pad, hs_split)
+    def log_softmax(self, hs_pad, hs_split=None, out=None):
+        lg = self.logits(hs_pad, hs_split, out)
         ops.log_softmax_rows_(lg.view(-1, self.odim))
         return lg
 

@@ -113,6 +113,7 @@ class TransformerDecoder(torch.nn.Module):
                 del self._ws[k]
             t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.after_norm.weight.device)
             self._ws[key] = t
+            self.buf_version = getattr(self, "buf_version", 0) + 1   # captured CUDA graphs hold these pointers
         return t
 
     # ---------------------------------------------------------------- device-side incremental scorer
@@ -141,8 +142,9 @@ class TransformerDecoder(torch.nn.Module):
         return self._ws[key]
 
     @torch.no_grad()
-    def step(self, st, pos, last_tok, anc, W):
+    def step(self, st, pos, last_tok, anc, W, step_ptr=None):
         """One decoding position for all n slots: returns log-probabilities [n][V] (buffer reused across steps).
+        With ``step_ptr`` (device int32) the position is ``pos + *step_ptr`` so that a captured CUDA graph can be replayed.
         Equivalent of batch_score/forward_one_step (transformer_decoder.py:262-311,191-238)."""
         pk = self._packed
         n, D, H, L, Uu = st["n"], self.d, self.heads, self.num_blocks, self.units
@@ -152,13 +154,13 @@ class TransformerDecoder(torch.nn.Module):
         ctx = self._buf("ctx", (2, n, D))
         q = self._buf("q", (n, D))
         h = self._buf("h", (2, n, Uu))
-        call("espb_dec_embed_f32", ptr(last_tok), ptr(pk["emb"]), ptr(st["pe"]), pos, n, D, math.sqrt(D), ptr(x))
+        call("espb_dec_embed_f32", ptr(last_tok), ptr(pk["emb"]), ptr(st["pe"]), pos, ptr(step_ptr), n, D, math.sqrt(D), ptr(x))
         _count()
         for li, w in enumerate(pk["layers"]):
             layernorm(x, *w["n1"], LN_EPS, out_split=xn)
             linear(xn, w["qkv_w"], qkv, bias=w["qkv_b"])
             call("espb_dec_self_attn_f32", ptr(qkv), ptr(st["kc"][li]), ptr(st["vc"][li]), ptr(anc), anc.shape[1], n, D, H, pos,
-                 ptr(ctx), n * D)
+                 ptr(step_ptr), st["max_len"], ptr(ctx), n * D)
             _count()
             linear(ctx, w["so_w"], x, bias=w["so_b"], residual=x)
             layernorm(x, *w["n2"], LN_EPS, out_split=xn)

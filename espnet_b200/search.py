@@ -61,15 +61,52 @@ class BatchBeamSearch(torch.nn.Module):
         if beam_size > 16 and self.decoder is not None:
             raise NotImplementedError("beam_size > 16 with an attention decoder")
 
+    # ---------------------------------------------------------------- search state (cached per shape so that CUDA graphs can be reused)
+    def _state(self, dev, U, Tmax, W, V, cap, mode, P):
+        key = (str(dev), U, Tmax, W, V, cap, mode, P)
+        cache = getattr(self, "_state_cache", None)
+        if cache is None:
+            cache = self._state_cache = {}
+        st = cache.get(key)
+        if st is not None:
+            return st
+        if len(cache) >= 4:
+            cache.clear()
+        n, PC = U * W, (P + 1 if mode == 1 else P)
+        i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)  # noqa: E731
+        f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)  # noqa: E731
+        ended_cap = W * cap
+        st = dict(
+            score=[f32(n), f32(n)], sc_dec=[f32(n), f32(n)], sc_ctc=[f32(n), f32(n)], active=[i32(n), i32(n)],
+            last_tok=[i32(n), i32(n)], parent=i32(n), anc=[i32(n, cap + 1), i32(n, cap + 1)],
+            bp_parent=i32(cap, n), bp_token=i32(cap, n), ended_cap=ended_cap,
+            e_count=i32(U), e_step=i32(U, ended_cap), e_slot=i32(U, ended_cap),
+            e_score=f32(U, ended_cap), e_dec=f32(U, ended_cap), e_ctc=f32(U, ended_cap),
+            best_at=f32(U, cap), best_all=f32(U), done=i32(U), cand_ids=i32(n, P), cand_val=f32(n, P), n_active=i32(1),
+            step=i32(1), lens32=i32(U), maxlen=i32(U), minlen=i32(U), graphs={}, graph_launches={})
+        if mode != 0:
+            st["logp_ctc"] = f32(U * Tmax, V)
+            st["r"] = [f32(n, Tmax, 4), f32(n, Tmax, 4)]   # per frame (r^n, r^b, r_sum, pad)
+            st["s_prev"] = [f32(n), f32(n)]
+            if mode == 1:
+                st["part"], st["psi"], st["valid"] = f32(n, PC), f32(n, PC), i32(n, PC)
+            else:
+                st["part"] = f32(n, V)
+        cache[key] = st
+        return st
+
+    use_cuda_graphs = True   # replay one captured graph per step parity once the buffers are warm (steps >= 4)
+
     @torch.no_grad()
     def forward_batch(self, enc, enc_lens, enc_split=None, maxlenratio=0.0, minlenratio=0.0, check_every=8):
         """enc (U, Tmax, D) CUDA, enc_lens (U,) -> list (per utterance) of n-best Hypothesis lists, sorted."""
+        from . import lib as _lib
+
         dev = enc.device
         U, Tmax, D = enc.shape
         W, V = self.beam_size, self.n_vocab
         n = U * W
         lens_cpu = enc_lens.detach().cpu().to(torch.int64)
-        lens32 = lens_cpu.to(device=dev, dtype=torch.int32)
         if maxlenratio == 0:
             maxlen = lens_cpu.clone()
         elif maxlenratio < 0:
@@ -78,105 +115,135 @@ class BatchBeamSearch(torch.nn.Module):
             maxlen = torch.clamp((maxlenratio * lens_cpu.double()).long(), min=1)
         minlen = torch.full_like(lens_cpu, -int(minlenratio)) if minlenratio < 0 else (minlenratio * lens_cpu.double()).long()
         cap = int(maxlen.max())
-        maxlen_d, minlen_d = maxlen.to(dev, torch.int32), minlen.to(dev, torch.int32)
         if enc_split is None:
             enc_split = ops.split_from(enc.contiguous().view(U * Tmax, D))
         use_dec, use_ctc = self.decoder is not None, self.ctc is not None
         mode = 1 if (use_dec and use_ctc) else (0 if use_dec else 2)
         P = self.pre_beam_size if mode == 1 else W
-        PC = P + 1 if mode == 1 else P
-        i32 = lambda *s, fill=0: torch.full(s, fill, dtype=torch.int32, device=dev)  # noqa: E731
-        f32 = lambda *s, fill=0.0: torch.full(s, fill, dtype=torch.float32, device=dev)  # noqa: E731
+        st = self._state(dev, U, Tmax, W, V, cap, mode, P)
 
-        # ---- state (double-buffered)
-        score, sc_dec, sc_ctc = [f32(n), f32(n)], [f32(n), f32(n)], [f32(n), f32(n)]
-        active = [i32(n), i32(n)]
-        active[0].view(U, W)[:, 0] = 1           # one initial hypothesis [sos] per utterance (batch_beam_search.py:124-153)
-        last_tok = [i32(n, fill=self.sos), i32(n, fill=self.sos)]
-        parent = i32(n)
-        anc = [i32(n, cap + 1), i32(n, cap + 1)]
-        bp_parent, bp_token = i32(cap, n, fill=-1), i32(cap, n, fill=self.eos)
-        ended_cap = W * cap
-        e_count, e_step, e_slot = i32(U), i32(U, ended_cap), i32(U, ended_cap)
-        e_score, e_dec, e_ctc = f32(U, ended_cap), f32(U, ended_cap), f32(U, ended_cap)
-        best_at, best_all, done = f32(U, cap, fill=float("-inf")), f32(U, fill=float("-inf")), i32(U)
-        cand_ids, cand_val = i32(n, P), f32(n, P)
-        n_active = i32(1)
-        dst = None
-        if use_dec:
-            dst = self.decoder.init_memory(enc_split, U, Tmax, lens32, n, cap)
-        logp_ctc = part = psi = valid = r = s_prev = None
+        # ---- (re)initialise the state in place: one hypothesis [sos] per utterance (batch_beam_search.py:124-153)
+        for k in ("score", "sc_dec", "sc_ctc", "active"):
+            st[k][0].zero_(); st[k][1].zero_()
+        st["active"][0].view(U, W)[:, 0] = 1
+        st["last_tok"][0].fill_(self.sos); st["last_tok"][1].fill_(self.sos)
+        st["bp_parent"].fill_(-1); st["bp_token"].fill_(self.eos)
+        st["e_count"].zero_(); st["done"].zero_()
+        st["best_at"].fill_(float("-inf")); st["best_all"].fill_(float("-inf"))
+        st["lens32"].copy_(lens_cpu.to(torch.int32)); st["maxlen"].copy_(maxlen.to(torch.int32)); st["minlen"].copy_(minlen.to(torch.int32))
+        st["step"].zero_()
+        lens32, step_dev = st["lens32"], st["step"]
+        score, sc_dec, sc_ctc, active, last_tok = st["score"], st["sc_dec"], st["sc_ctc"], st["active"], st["last_tok"]
+        parent, anc = st["parent"], st["anc"]
+        dst = self.decoder.init_memory(enc_split, U, Tmax, lens32, n, cap) if use_dec else None
+        logp_ctc = r = s_prev = None
         if use_ctc:
-            logp_ctc = self.ctc.log_softmax(enc, enc_split)           # (U, Tmax, V), scorers/ctc.py:96-99
-            r = [f32(n, Tmax, 4), f32(n, Tmax, 4)]   # per frame (r^n, r^b, r_sum, pad)
-            s_prev = [f32(n), f32(n)]
+            logp_ctc = self.ctc.log_softmax(enc, enc_split, out=st["logp_ctc"])   # (U, Tmax, V), scorers/ctc.py:96-99
+            r, s_prev = st["r"], st["s_prev"]
             call("espb_ctc_init_state_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, W, ptr(r[0]), ptr(s_prev[0]))
             _count()
-            if mode == 1:
-                part, psi, valid = f32(n, PC), f32(n, PC), i32(n, PC)
-            else:
-                part = f32(n, V)
         end_detect = 1 if maxlenratio == 0.0 else 0
-        # the CTC state update of step i is only consumed by the CTC scoring of step i+1 (after the next decoder pass): run it on a
-        # side stream so that its T-step sequential recursion overlaps the decoder
-        main = torch.cuda.current_stream()
         side = self._side_stream(dev) if (use_ctc and use_dec) else None
-        ev_sel, ev_adv = torch.cuda.Event(), torch.cuda.Event()
-        adv_pending = False
-        cur = 0
-        steps_run = 0
-        for i in range(cap):
+
+        def step_body(i, cur, sp):
+            """One search step. `sp` is None (host step index i) or the device step counter (graph mode: i is ignored)."""
             nxt = cur ^ 1
-            logp_dec = None
-            if use_dec:
-                logp_dec = self.decoder.step(dst, i, last_tok[cur], anc[cur], W)
-            if adv_pending:
-                main.wait_event(ev_adv)
-                adv_pending = False
+            iv = 0 if sp is not None else i
+            main = torch.cuda.current_stream()
+            forked = False
+            if use_ctc and (sp is not None or i >= 1):
+                # CTC forward variables of the hypotheses chosen in the previous step (scorers/ctc.py:40-63): only the scoring below needs
+                # them, so the T-step recursion runs on a side stream concurrently with the decoder pass
+                def advance():
+                    call("espb_ctc_advance_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[nxt]), ptr(parent),
+                         ptr(last_tok[nxt]), ptr(last_tok[cur]), ptr(active[cur]), iv - 1, ptr(sp), ptr(r[cur]), ptr(s_prev[cur]))
+                    _count()
+                if side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    with torch.cuda.stream(side):
+                        side.wait_event(ev)
+                        advance()
+                    forked = True
+                else:
+                    advance()
+            logp_dec = self.decoder.step(dst, iv, last_tok[cur], anc[cur], W, sp) if use_dec else None
+            if forked:
+                main.wait_stream(side)
             if mode == 1:
-                ops.rows_topk(logp_dec, self.w_dec, P, cand_ids, cand_val)
+                ops.rows_topk(logp_dec, self.w_dec, P, st["cand_ids"], st["cand_val"])
                 call("espb_ctc_score_cands_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
-                     ptr(last_tok[cur]), i, ptr(cand_ids), P, ptr(part), ptr(psi), ptr(valid))
+                     ptr(last_tok[cur]), iv, ptr(sp), ptr(st["cand_ids"]), P, ptr(st["part"]), ptr(st["psi"]), ptr(st["valid"]))
                 _count()
             elif mode == 0:
-                ops.rows_topk(logp_dec, self.w_dec, P, cand_ids, cand_val)
+                ops.rows_topk(logp_dec, self.w_dec, P, st["cand_ids"], st["cand_val"])
             else:
                 call("espb_ctc_score_dense_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
-                     ptr(last_tok[cur]), i, ptr(part))
+                     ptr(last_tok[cur]), i, ptr(st["part"]))
                 _count()
-                ops.rows_topk(part, self.w_ctc, P, cand_ids, cand_val)
+                ops.rows_topk(st["part"], self.w_ctc, P, st["cand_ids"], st["cand_val"])
             call("espb_beam_select", ptr(score[cur]), ptr(sc_dec[cur]), ptr(sc_ctc[cur]), ptr(active[cur]), ptr(score[nxt]),
-                 ptr(sc_dec[nxt]), ptr(sc_ctc[nxt]), ptr(active[nxt]), ptr(last_tok[nxt]), ptr(parent), ptr(bp_parent), ptr(bp_token),
-                 ptr(e_count), ptr(e_step), ptr(e_slot), ptr(e_score), ptr(e_dec), ptr(e_ctc), ended_cap, ptr(best_at), ptr(best_all),
-                 ptr(done), U, W, P, V, i, ptr(maxlen_d), ptr(minlen_d), self.eos, self.w_dec, self.w_ctc, self.penalty, mode,
-                 ptr(cand_ids), ptr(cand_val), ptr(logp_dec), ptr(part), ptr(valid), end_detect, cap)
+                 ptr(sc_dec[nxt]), ptr(sc_ctc[nxt]), ptr(active[nxt]), ptr(last_tok[nxt]), ptr(parent), ptr(st["bp_parent"]),
+                 ptr(st["bp_token"]), ptr(st["e_count"]), ptr(st["e_step"]), ptr(st["e_slot"]), ptr(st["e_score"]), ptr(st["e_dec"]),
+                 ptr(st["e_ctc"]), st["ended_cap"], ptr(st["best_at"]), ptr(st["best_all"]), ptr(st["done"]), U, W, P, V, iv, ptr(sp),
+                 ptr(st["maxlen"]), ptr(st["minlen"]), self.eos, self.w_dec, self.w_ctc, self.penalty, mode, ptr(st["cand_ids"]),
+                 ptr(st["cand_val"]), ptr(logp_dec), ptr(st.get("part")), ptr(st.get("valid")), end_detect, cap)
             _count()
             if use_dec:
-                call("espb_anc_update_i32", ptr(anc[cur]), ptr(anc[nxt]), cap + 1, ptr(parent), i, n)
+                call("espb_anc_update_i32", ptr(anc[cur]), ptr(anc[nxt]), cap + 1, ptr(parent), iv, ptr(sp), n)
                 _count()
-            if use_ctc:
-                if side is not None:
-                    ev_sel.record(main)
-                    with torch.cuda.stream(side):
-                        side.wait_event(ev_sel)
-                        call("espb_ctc_advance_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(parent),
-                             ptr(last_tok[cur]), ptr(last_tok[nxt]), ptr(active[nxt]), i, ptr(r[nxt]), ptr(s_prev[nxt]))
-                        ev_adv.record(side)
-                    adv_pending = True
-                else:
-                    call("espb_ctc_advance_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(parent),
-                         ptr(last_tok[cur]), ptr(last_tok[nxt]), ptr(active[nxt]), i, ptr(r[nxt]), ptr(s_prev[nxt]))
+            if sp is not None:
+                call("espb_step_inc_i32", ptr(sp))
                 _count()
-            cur = nxt
+
+        graphs_ok = (self.use_cuda_graphs and mode != 2 and cap >= 8 and _lib.profile is None and ops.gemm_profile is None)
+        steps_run = 0
+        buf_ver = (getattr(self.decoder, "buf_version", 0), id(self.decoder._packed)) if use_dec else None
+        for i in range(cap):
+            cur = i & 1
+            if graphs_ok and i >= 2:
+                if st.get("graph_buf_ver") != buf_ver:   # decoder buffers / packed weights were re-created: captured pointers are stale
+                    st["graphs"].clear()
+                    st["graph_buf_ver"] = buf_ver
+                g = st["graphs"].get(cur)
+                if g is None:      # capture this parity once (steps 2 and 3); nothing executes during capture, so replay right after
+                    step_dev.fill_(i)
+                    g = torch.cuda.CUDAGraph()
+                    cs = self._capture_stream(dev)
+                    cs.wait_stream(torch.cuda.current_stream())
+                    before = ops.launch_counter[0]
+                    with torch.cuda.stream(cs):
+                        g.capture_begin()
+                        step_body(i, cur, step_dev)
+                        g.capture_end()
+                    torch.cuda.current_stream().wait_stream(cs)
+                    st["graph_launches"][cur] = ops.launch_counter[0] - before
+                    ops.launch_counter[0] = before
+                    st["graphs"][cur] = g
+                elif i == 2:
+                    step_dev.fill_(i)  # graphs cached from an earlier call: (re)position the device step counter
+                g.replay()
+                ops.launch_counter[0] += st["graph_launches"][cur]
+            else:
+                step_body(i, cur, None)
             steps_run = i + 1
             if (i + 1) % check_every == 0 or end_detect:
-                call("espb_count_active_i32", ptr(active[cur]), n, ptr(n_active))
+                call("espb_count_active_i32", ptr(active[(i + 1) & 1]), n, ptr(st["n_active"]))
                 _count()
-                if int(n_active.item()) == 0:
+                if int(st["n_active"].item()) == 0:
                     break
         if side is not None:
-            main.wait_stream(side)
-        return self._collect(U, W, steps_run, maxlen, bp_parent, bp_token, e_count, e_step, e_slot, e_score, e_dec, e_ctc)
+            torch.cuda.current_stream().wait_stream(side)
+        return self._collect(U, W, steps_run, maxlen, st["bp_parent"], st["bp_token"], st["e_count"], st["e_step"], st["e_slot"],
+                             st["e_score"], st["e_dec"], st["e_ctc"])
+
+    def _capture_stream(self, dev):
+        if not hasattr(self, "_cap_streams"):
+            self._cap_streams = {}
+        key = str(dev)
+        if key not in self._cap_streams:
+            self._cap_streams[key] = torch.cuda.Stream(device=dev)
+        return self._cap_streams[key]
 
     def _side_stream(self, dev):
         key = str(dev)

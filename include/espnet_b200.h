@@ -97,9 +97,12 @@ int espb_ctc_collapse_i32(const int* argmax, int B, int Tmax, const int* lens, i
 
 /* ---- Decoder step (transformer_decoder.py:191-311, decoder_layer.py:73-179, embedding.py:38-95) -------------------------
  * Slots n = U*W (utterance-major). Self-attention cache kc/vc [Lmax][n][D] addressed through anc [n][anc_ld]. */
-int espb_dec_embed_f32(const int* last_tok, const float* emb, const float* pe, int pos, int n, int D, float scale, float* x, cudaStream_t stream);
-int espb_dec_self_attn_f32(const float* qkv, float* kc, float* vc, const int* anc, int anc_ld, int n, int D, int H, int pos, float* ctx,
-                           long long ctx_plane, cudaStream_t stream);
+/* Step-dependent integers (pos / step / out_len) are passed as `value` plus an optional device pointer `step_ptr`: the kernel uses
+ * value + *step_ptr when step_ptr != NULL, so one CUDA graph of a decoding step can be replayed for every position. */
+int espb_dec_embed_f32(const int* last_tok, const float* emb, const float* pe, int pos, const int* step_ptr, int n, int D, float scale, float* x,
+                       cudaStream_t stream);
+int espb_dec_self_attn_f32(const float* qkv, float* kc, float* vc, const int* anc, int anc_ld, int n, int D, int H, int pos, const int* step_ptr,
+                           int max_pos, float* ctx, long long ctx_plane, cudaStream_t stream);
 /* kmem / vmem: [U][H][Tmax][dk] blocks of one decoder layer (projected once per utterance). */
 int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, int U, int Tmax, const int* lens, int W, int D, int H, float* ctx,
                           long long ctx_plane, cudaStream_t stream);
@@ -112,23 +115,24 @@ int espb_rows_topk_f32(const float* x, long long rows, long long ld, int V, floa
 int espb_ctc_init_state_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int W, float* r, float* s_prev,
                             cudaStream_t stream);
 int espb_ctc_score_cands_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
-                             const float* s_prev, const int* last_tok, int out_len, const int* cand, int P, float* part, float* psi,
-                             int* valid, cudaStream_t stream);
+                             const float* s_prev, const int* last_tok, int out_len, const int* step_ptr, const int* cand, int P, float* part,
+                             float* psi, int* valid, cudaStream_t stream);
 int espb_ctc_score_dense_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
                              const float* s_prev, const int* last_tok, int out_len, float* part, cudaStream_t stream);
 int espb_ctc_advance_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
-                         const int* parent, const int* par_last_tok, const int* new_tok, const int* new_active, int out_len, float* r_new,
-                         float* s_new, cudaStream_t stream);
+                         const int* parent, const int* par_last_tok, const int* new_tok, const int* new_active, int out_len, const int* step_ptr,
+                         float* r_new, float* s_new, cudaStream_t stream);
 /* Weighted sum + beam top-k over (hyps x candidates) per utterance + post_process (eos / maxlen / minlen / end_detect).
  * mode 0 decoder only, 1 joint (pre-beam candidates + eos), 2 CTC only (dense). */
 int espb_beam_select(const float* score, const float* sc_dec, const float* sc_ctc, const int* active, float* n_score, float* n_sc_dec,
                      float* n_sc_ctc, int* n_active, int* n_last_tok, int* n_parent, int* bp_parent, int* bp_token, int* ended_count,
                      int* ended_step, int* ended_slot, float* ended_score, float* ended_dec, float* ended_ctc, int ended_cap,
-                     float* best_at_step, float* best_all, int* utt_done, int U, int W, int P, int V, int step, const int* maxlen,
-                     const int* minlen, int eos, float w_dec, float w_ctc, float penalty, int mode, const int* cand_ids,
+                     float* best_at_step, float* best_all, int* utt_done, int U, int W, int P, int V, int step, const int* step_ptr,
+                     const int* maxlen, const int* minlen, int eos, float w_dec, float w_ctc, float penalty, int mode, const int* cand_ids,
                      const float* cand_val, const float* logp_dec, const float* part, const int* valid, int end_detect, int maxlen_cap,
                      cudaStream_t stream);
-int espb_anc_update_i32(const int* anc, int* n_anc, int anc_ld, const int* parent, int pos, int n, cudaStream_t stream);
+int espb_anc_update_i32(const int* anc, int* n_anc, int anc_ld, const int* parent, int pos, const int* step_ptr, int n, cudaStream_t stream);
+int espb_step_inc_i32(int* step, cudaStream_t stream);
 int espb_count_active_i32(const int* active, int n, int* out, cudaStream_t stream);
 
 #ifdef __cplusplus
