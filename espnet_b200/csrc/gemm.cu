@@ -302,22 +302,25 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   constexpr int B_TILE_BYTES = BH * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   constexpr int CW = BN / 2;                      // accumulator columns per epilogue warp
+  constexpr int XP_FLOATS = 32 * 33;              // per-warp transpose buffer of the coalescing epilogue
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t xp_base = smem_base + STAGES * STAGE_BYTES;            // 8 warps x [32][33] floats
+  const uint32_t bar_base = xp_base + 8 * XP_FLOATS * 4;
   const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * STAGES;
   const uint32_t tfull_bar = bar_base + 16 * STAGES, tempty_bar = tfull_bar + 16;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 16 * STAGES + 32);
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + (bar_base - smem_base) + 16 * STAGES + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1;
-  const int m0 = pair * 256 + (int)rank * 128;
-  const int n0 = blockIdx.y * BN;
-  const int bx = blockIdx.z % p.nbx, by = blockIdx.z / p.nbx;
   const int num_kb = (p.K + BK - 1) / BK;
   const int num_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
+  // persistent tile loop: pair `pair` takes tiles pair, pair + num_pairs, ...; m fastest so that concurrently running pairs share B tiles
+  const int tiles_m = (p.M + 255) / 256, tiles_n = (p.N + BN - 1) / BN;
+  const long long total_tiles = (long long)tiles_m * tiles_n * p.nbx * p.nby;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
@@ -340,119 +343,123 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     if (lane == 0) {
       const int cblk = (p.a_mode == 1) ? p.cv_cin / BK : 0;
       const uint32_t leader_full = full_bar & 0xFEFFFFFFu;   // same offset in the even (leader) CTA of the pair
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        if (leader) mbar_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);  // bytes of both CTAs land on the leader's barrier
-        const uint32_t fb = leader_full + 8 * s;
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        if (p.a_mode == 0) {
-          const int ko = (p.kob > 0) ? kb / p.kob : 0;
-          const int ki = (p.kob > 0) ? kb % p.kob : kb;
-          tma_load_5d_2sm(sa, &tmA, fb, ki * BK, m0, bx * axm + ko, by * aym, 0);
-          tma_load_5d_2sm(sa + A_TILE_BYTES, &tmA, fb, ki * BK, m0, bx * axm + ko, by * aym, 1);
-        } else {
-          const int tap = kb / cblk, c0 = (kb % cblk) * BK;
-          const int kt = tap / 3, kf = tap % 3;
-          const int par = (kt & 1) * 2 + (kf & 1);
-          tma_load_5d_2sm(sa, &tmA, fb, c0, m0 + (kt >> 1), bx + (kf >> 1), par, by);
-          tma_load_5d_2sm(sa + A_TILE_BYTES, &tmA, fb, c0, m0 + (kt >> 1), bx + (kf >> 1), 4 + par, by);
+      long long g = 0;                                        // global k-block counter (stage ring position)
+      for (long long tile = pair; tile < total_tiles; tile += num_pairs) {
+        const int mt = (int)(tile % tiles_m);
+        const int nt = (int)((tile / tiles_m) % tiles_n);
+        const int z = (int)(tile / ((long long)tiles_m * tiles_n));
+        const int bx = z % p.nbx, by = z / p.nbx;
+        const int m0 = mt * 256 + (int)rank * 128, nb = nt * BN + (int)rank * BH;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = (int)(g % STAGES);
+          const uint32_t ph = (uint32_t)((g / STAGES) & 1);
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          if (leader) mbar_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);  // bytes of both CTAs land on the leader's barrier
+          const uint32_t fb = leader_full + 8 * s;
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          if (p.a_mode == 0) {
+            const int ko = (p.kob > 0) ? kb / p.kob : 0;
+            const int ki = (p.kob > 0) ? kb % p.kob : kb;
+            tma_load_5d_2sm(sa, &tmA, fb, ki * BK, m0, bx * axm + ko, by * aym, 0);
+            tma_load_5d_2sm(sa + A_TILE_BYTES, &tmA, fb, ki * BK, m0, bx * axm + ko, by * aym, 1);
+          } else {
+            const int tap = kb / cblk, c0 = (kb % cblk) * BK;
+            const int kt = tap / 3, kf = tap % 3;
+            const int par = (kt & 1) * 2 + (kf & 1);
+            tma_load_5d_2sm(sa, &tmA, fb, c0, m0 + (kt >> 1), bx + (kf >> 1), par, by);
+            tma_load_5d_2sm(sa + A_TILE_BYTES, &tmA, fb, c0, m0 + (kt >> 1), bx + (kf >> 1), 4 + par, by);
+          }
+          tma_load_5d_2sm(sa + 2 * A_TILE_BYTES, &tmB, fb, kb * BK, nb, bx * bxm, by * bym, 0);
+          tma_load_5d_2sm(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB, fb, kb * BK, nb, bx * bxm, by * bym, 1);
         }
-        const int nb = n0 + (int)rank * BH;
-        tma_load_5d_2sm(sa + 2 * A_TILE_BYTES, &tmB, fb, kb * BK, nb, bx * bxm, by * bym, 0);
-        tma_load_5d_2sm(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB, fb, kb * BK, nb, bx * bxm, by * bym, 1);
       }
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      for (int c = 0; c < num_chunks; ++c) {
-        const int b = c & 1;
-        mbar_wait(tempty_bar + 8 * b, ((c >> 1) & 1) ^ 1);   // both CTAs' epilogues have drained this accumulator buffer
-        tcgen05_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(b * BN);
-        const int kb_end = min(num_kb, (c + 1) * CHUNK_KB);
-        for (int kb = c * CHUNK_KB; kb < kb_end; ++kb) {
-          const int s = kb % STAGES;
-          const uint32_t ph = (kb / STAGES) & 1;
-          mbar_wait(full_bar + 8 * s, ph);
+      long long g = 0, cg = 0;                                // global k-block / chunk counters
+      for (long long tile = pair; tile < total_tiles; tile += num_pairs) {
+        for (int c = 0; c < num_chunks; ++c, ++cg) {
+          const int b = (int)(cg & 1);
+          mbar_wait(tempty_bar + 8 * b, (uint32_t)(((cg >> 1) & 1) ^ 1));   // both CTAs' epilogues have drained this accumulator buffer
           tcgen05_fence_after();
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t d = tmem_base + (uint32_t)(b * BN);
+          const int kb_end = min(num_kb, (c + 1) * CHUNK_KB);
+          for (int kb = c * CHUNK_KB; kb < kb_end; ++kb, ++g) {
+            const int s = (int)(g % STAGES);
+            const uint32_t ph = (uint32_t)((g / STAGES) & 1);
+            mbar_wait(full_bar + 8 * s, ph);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_base + s * STAGE_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
-            const uint64_t b_hi = umma_desc(sa + 2 * A_TILE_BYTES + k * 32);
-            const uint64_t b_lo = umma_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + k * 32);
-            mma_tf32_2sm(d, a_lo, b_hi, idesc, (kb != c * CHUNK_KB || k != 0) ? 1u : 0u);
-            mma_tf32_2sm(d, a_hi, b_lo, idesc, 1);
-            mma_tf32_2sm(d, a_hi, b_hi, idesc, 1);
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
+              const uint64_t b_hi = umma_desc(sa + 2 * A_TILE_BYTES + k * 32);
+              const uint64_t b_lo = umma_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + k * 32);
+              mma_tf32_2sm(d, a_lo, b_hi, idesc, (kb != c * CHUNK_KB || k != 0) ? 1u : 0u);
+              mma_tf32_2sm(d, a_hi, b_lo, idesc, 1);
+              mma_tf32_2sm(d, a_hi, b_hi, idesc, 1);
+            }
+            tcgen05_commit_2sm(empty_bar + 8 * s);
           }
-          tcgen05_commit_2sm(empty_bar + 8 * s);
+          tcgen05_commit_2sm(tfull_bar + 8 * b);
         }
-        tcgen05_commit_2sm(tfull_bar + 8 * b);
       }
     }
   } else {
     const int e = warp - 2, q = warp & 3, half = e >> 2;   // a warp may only touch TMEM lanes 32*(warp_id%4)..+31
-    float acc[CW];
+    float* xp = reinterpret_cast<float*>(smem_al + (xp_base - smem_base)) + e * XP_FLOATS;
+    long long cg = 0;
+    for (long long tile = pair; tile < total_tiles; tile += num_pairs) {
+      const int mt = (int)(tile % tiles_m);
+      const int nt = (int)((tile / tiles_m) % tiles_n);
+      const int z = (int)(tile / ((long long)tiles_m * tiles_n));
+      const int bx = z % p.nbx, by = z / p.nbx;
+      const int m0 = mt * 256 + (int)rank * 128, n0 = nt * BN;
+      float acc[CW];
 #pragma unroll
-    for (int j = 0; j < CW; ++j) acc[j] = 0.f;
-    for (int c = 0; c < num_chunks; ++c) {
-      const int b = c & 1;
-      mbar_wait(tfull_bar + 8 * b, (c >> 1) & 1);
-      tcgen05_fence_after();
+      for (int j = 0; j < CW; ++j) acc[j] = 0.f;
+      for (int c = 0; c < num_chunks; ++c, ++cg) {
+        const int b = (int)(cg & 1);
+        mbar_wait(tfull_bar + 8 * b, (uint32_t)((cg >> 1) & 1));
+        tcgen05_fence_after();
+#pragma unroll
+        for (int j = 0; j < CW / 32; ++j) {
+          float v[32];
+          __syncwarp();
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + half * CW + j * 32), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * b, 0);   // leader CTA's barrier (local or remote)
+      }
+      // ---- epilogue: transpose 32x32 blocks through smem so that every global access of a warp is one 128-byte row segment
+      EpiArgs ea;
+      const long long coff = (long long)by * p.sc_y + (long long)bx * p.sc_x;
+      ea.C = p.C + coff; ea.c_plane = p.c_plane; ea.ldc = p.ldc; ea.split_out = p.split_out;
+      ea.bias = p.bias ? p.bias + (long long)bx * p.sbias_x : nullptr; ea.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
+      ea.ldr = p.ldr; ea.alpha = p.alpha; ea.act = p.act;
+      const int row0 = m0 + q * 32;
 #pragma unroll
       for (int j = 0; j < CW / 32; ++j) {
-        float v[32];
-        __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + half * CW + j * 32), v);
+        const int col = n0 + half * CW + j * 32 + lane;
+        if (row0 < p.M && n0 + half * CW + j * 32 < p.N) {          // warp-uniform: skip blocks entirely outside the matrix
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * b, 0);   // leader CTA's barrier (local or remote)
-    }
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    EpiArgs ea;
-    const long long coff = (long long)by * p.sc_y + (long long)bx * p.sc_x;
-    ea.C = p.C + coff; ea.c_plane = p.c_plane; ea.ldc = p.ldc; ea.split_out = p.split_out;
-    ea.bias = p.bias ? p.bias + (long long)bx * p.sbias_x : nullptr; ea.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
-    ea.ldr = p.ldr; ea.alpha = p.alpha; ea.act = p.act;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((coff & 3) == 0) && ((p.c_plane & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    if (row_ok) {
-      float* crow = ea.C + (long long)row * ea.ldc;
-      const int colbase = n0 + half * CW;
-#pragma unroll
-      for (int j = 0; j < CW; j += 4) {
-        const int col0 = colbase + j;
-        if (col0 >= p.N) continue;
-        if (vec_ok && col0 + 4 <= p.N) {
-          float t0 = epi_value(ea, acc[j], row, col0), t1 = epi_value(ea, acc[j + 1], row, col0 + 1);
-          float t2 = epi_value(ea, acc[j + 2], row, col0 + 2), t3 = epi_value(ea, acc[j + 3], row, col0 + 3);
-          float4 o, l;
-          if (ea.split_out) {
-            o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
-            l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
-            *reinterpret_cast<float4*>(crow + col0) = o;
-            *reinterpret_cast<float4*>(crow + ea.c_plane + col0) = l;
-          } else {
-            o.x = t0; o.y = t1; o.z = t2; o.w = t3;
-            *reinterpret_cast<float4*>(crow + col0) = o;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int col = col0 + i;
-            if (col < p.N) {
-              float t = epi_value(ea, acc[j + i], row, col);
-              if (ea.split_out) { float h = espb::tf32_hi(t); crow[col] = h; crow[ea.c_plane + col] = espb::tf32_lo(t, h); }
-              else crow[col] = t;
+          for (int i = 0; i < 32; ++i) xp[lane * 33 + i] = acc[j * 32 + i];
+          __syncwarp();
+          const int rmax = min(32, p.M - row0);
+          if (col < p.N) {
+            for (int rr = 0; rr < rmax; ++rr) {
+              const long long row = row0 + rr;
+              const float t = epi_value(ea, xp[rr * 33 + lane], row, col);
+              float* cp = ea.C + row * ea.ldc + col;
+              if (ea.split_out) { const float h = espb::tf32_hi(t); cp[0] = h; cp[ea.c_plane] = espb::tf32_lo(t, h); }
+              else cp[0] = t;
             }
           }
+          __syncwarp();
         }
       }
     }
@@ -602,16 +609,23 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc
 
 template <int BN, int STAGES>
 int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
-  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * (BN / 2) * 128) + 1024 + 16 * STAGES + 64;
+  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * (BN / 2) * 128) + 8 * 32 * 33 * 4 + 1024 + 16 * STAGES + 64;
+  static_assert(smem <= 232448, "dynamic shared memory budget exceeded");
   static bool attr_set = false;
+  static int num_sms = 0;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tf32x3_2cta_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       espb_set_error("cudaFuncSetAttribute(max dynamic smem) failed");
       return ESPB_ERR_CUDA;
     }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     attr_set = true;
   }
-  dim3 grid(2 * ((d.M + 255) / 256), (d.N + BN - 1) / BN, d.nbx * d.nby);
+  const long long tiles = (long long)((d.M + 255) / 256) * ((d.N + BN - 1) / BN) * d.nbx * d.nby;
+  const long long pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;   // persistent: one CTA pair per SM pair
+  dim3 grid((unsigned)(2 * pairs), 1, 1);
   gemm_tf32x3_2cta_kernel<BN, STAGES><<<grid, V2_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
