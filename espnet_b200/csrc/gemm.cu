@@ -302,7 +302,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   constexpr int B_TILE_BYTES = BH * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   constexpr int CW = BN / 2;                      // accumulator columns per epilogue warp
-  constexpr int XP_FLOATS = 32 * 33;              // per-warp transpose buffer of the coalescing epilogue
+  constexpr int XP_FLOATS = 16 * 36;              // per-warp transpose buffer of the coalescing epilogue (16 rows x 32 cols, padded)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t xp_base = smem_base + STAGES * STAGE_BYTES;            // 8 warps x [32][33] floats
@@ -435,31 +435,81 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(tempty_bar + 8 * b, 0);   // leader CTA's barrier (local or remote)
       }
-      // ---- epilogue: transpose 32x32 blocks through smem so that every global access of a warp is one 128-byte row segment
+      // ---- epilogue: 32x32 blocks are transposed through smem (two 16-row halves) so that every global access of a warp covers four
+      // 128-byte row segments with 128-bit accesses; residual and bias values are fetched before the math so that loads overlap.
       EpiArgs ea;
       const long long coff = (long long)by * p.sc_y + (long long)bx * p.sc_x;
+      const long long roff = (long long)by * p.sr_y + (long long)bx * p.sr_x;
       ea.C = p.C + coff; ea.c_plane = p.c_plane; ea.ldc = p.ldc; ea.split_out = p.split_out;
-      ea.bias = p.bias ? p.bias + (long long)bx * p.sbias_x : nullptr; ea.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
+      ea.bias = p.bias ? p.bias + (long long)bx * p.sbias_x : nullptr; ea.R = p.R ? p.R + roff : nullptr;
       ea.ldr = p.ldr; ea.alpha = p.alpha; ea.act = p.act;
+      const bool vec_ok = ((p.ldc & 3) == 0) && ((coff & 3) == 0) && ((p.c_plane & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                          (!p.R || (((p.ldr & 3) == 0) && ((roff & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0))) &&
+                          (!p.bias || ((((long long)bx * p.sbias_x) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
       const int row0 = m0 + q * 32;
+      const int rsub = lane >> 3, c4 = (lane & 7) * 4;     // read mapping: 4 rows x 8 float4 per warp access
 #pragma unroll
       for (int j = 0; j < CW / 32; ++j) {
-        const int col = n0 + half * CW + j * 32 + lane;
-        if (row0 < p.M && n0 + half * CW + j * 32 < p.N) {          // warp-uniform: skip blocks entirely outside the matrix
+        const int colb = n0 + half * CW + j * 32;
+        if (row0 >= p.M || colb >= p.N) continue;            // warp-uniform: block entirely outside the matrix
+        const int col = colb + c4;
+        const bool full4 = vec_ok && (col + 3 < p.N);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ea.bias && full4) b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col));
 #pragma unroll
-          for (int i = 0; i < 32; ++i) xp[lane * 33 + i] = acc[j * 32 + i];
+        for (int hh = 0; hh < 2; ++hh) {                     // rows hh*16 .. hh*16+15 of the block
           __syncwarp();
-          const int rmax = min(32, p.M - row0);
-          if (col < p.N) {
-            for (int rr = 0; rr < rmax; ++rr) {
-              const long long row = row0 + rr;
-              const float t = epi_value(ea, xp[rr * 33 + lane], row, col);
-              float* cp = ea.C + row * ea.ldc + col;
-              if (ea.split_out) { const float h = espb::tf32_hi(t); cp[0] = h; cp[ea.c_plane] = espb::tf32_lo(t, h); }
-              else cp[0] = t;
-            }
+          if ((lane >> 4) == hh) {
+            float* w = xp + (lane & 15) * 36;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(w + i) = make_float4(acc[j * 32 + i], acc[j * 32 + i + 1], acc[j * 32 + i + 2], acc[j * 32 + i + 3]);
           }
           __syncwarp();
+          float4 rv[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const long long row = row0 + hh * 16 + it * 4 + rsub;
+            rv[it] = (ea.R && full4 && row < p.M) ? *reinterpret_cast<const float4*>(ea.R + row * ea.ldr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rl = it * 4 + rsub;
+            const long long row = row0 + hh * 16 + rl;
+            if (row >= p.M) continue;
+            const float4 v = *reinterpret_cast<const float4*>(xp + rl * 36 + c4);
+            float* cp = ea.C + row * ea.ldc + col;
+            if (full4) {
+              float t[4] = {v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w};
+              const float rr4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float x = t[i];
+                if (ea.act == espb::ACT_RELU) x = fmaxf(x, 0.f);
+                else if (ea.act == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
+                t[i] = fmaf(ea.alpha, x, rr4[i]);
+              }
+              if (ea.split_out) {
+                float4 h, l;
+                h.x = espb::tf32_hi(t[0]); h.y = espb::tf32_hi(t[1]); h.z = espb::tf32_hi(t[2]); h.w = espb::tf32_hi(t[3]);
+                l.x = espb::tf32_lo(t[0], h.x); l.y = espb::tf32_lo(t[1], h.y); l.z = espb::tf32_lo(t[2], h.z); l.w = espb::tf32_lo(t[3], h.w);
+                *reinterpret_cast<float4*>(cp) = h;
+                *reinterpret_cast<float4*>(cp + ea.c_plane) = l;
+              } else {
+                *reinterpret_cast<float4*>(cp) = make_float4(t[0], t[1], t[2], t[3]);
+              }
+            } else {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (col + i < p.N) {
+                  const float tt = epi_value(ea, vv[i], row, col + i);
+                  if (ea.split_out) { const float hh2 = espb::tf32_hi(tt); cp[i] = hh2; cp[ea.c_plane + i] = espb::tf32_lo(tt, hh2); }
+                  else cp[i] = tt;
+                }
+              }
+            }
+          }
         }
       }
     }
@@ -609,7 +659,7 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc
 
 template <int BN, int STAGES>
 int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
-  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * (BN / 2) * 128) + 8 * 32 * 33 * 4 + 1024 + 16 * STAGES + 64;
+  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * (BN / 2) * 128) + 8 * 16 * 36 * 4 + 1024 + 16 * STAGES + 64;
   static_assert(smem <= 232448, "dynamic shared memory budget exceeded");
   static bool attr_set = false;
   static int num_sms = 0;
