@@ -317,7 +317,8 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const bool leader = rank == 0;
   const int num_kb = (p.K + BK - 1) / BK;
   const int num_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
-  // persistent tile loop: pair `pair` takes tiles pair, pair + num_pairs, ...; m fastest so that concurrently running pairs share B tiles
+  // persistent tile loop: pair `pair` takes tiles pair, pair + num_pairs, ...; n fastest, so the pairs running concurrently cover all
+  // n-tiles of a few m-tiles: each A panel is fetched from HBM once and the (small) B operand stays L2-resident
   const int tiles_m = (p.M + 255) / 256, tiles_n = (p.N + BN - 1) / BN;
   const long long total_tiles = (long long)tiles_m * tiles_n * p.nbx * p.nby;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -345,8 +346,8 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const uint32_t leader_full = full_bar & 0xFEFFFFFFu;   // same offset in the even (leader) CTA of the pair
       long long g = 0;                                        // global k-block counter (stage ring position)
       for (long long tile = pair; tile < total_tiles; tile += num_pairs) {
-        const int mt = (int)(tile % tiles_m);
-        const int nt = (int)((tile / tiles_m) % tiles_n);
+        const int nt = (int)(tile % tiles_n);
+        const int mt = (int)((tile / tiles_n) % tiles_m);
         const int z = (int)(tile / ((long long)tiles_m * tiles_n));
         const int bx = z % p.nbx, by = z / p.nbx;
         const int m0 = mt * 256 + (int)rank * 128, nb = nt * BN + (int)rank * BH;
@@ -411,8 +412,8 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     float* xp = reinterpret_cast<float*>(smem_al + (xp_base - smem_base)) + e * XP_FLOATS;
     long long cg = 0;
     for (long long tile = pair; tile < total_tiles; tile += num_pairs) {
-      const int mt = (int)(tile % tiles_m);
-      const int nt = (int)((tile / tiles_m) % tiles_n);
+      const int nt = (int)(tile % tiles_n);
+      const int mt = (int)((tile / tiles_n) % tiles_m);
       const int z = (int)(tile / ((long long)tiles_m * tiles_n));
       const int bx = z % p.nbx, by = z / p.nbx;
       const int m0 = mt * 256 + (int)rank * 128, n0 = nt * BN;
@@ -706,7 +707,7 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
   if (rc != ESPB_OK) return rc;
   const int bxm = d.sb_x != 0 ? 1 : 0, bym = d.sb_y != 0 ? 1 : 0;
   const long long tiles_m = (d.M + BM - 1) / BM, nb = (long long)d.nbx * d.nby;
-  if (version == 2) {
+  if (version == 2 && d.M > 1024) {   // small-M (decode) problems are latency-bound: the 128x64 1-CTA tiles spread them over more SMs
     // CTA-pair kernel: 256 x BN tiles; B box = BN/2 rows per CTA
     const int bn = (d.N <= 128) ? 128 : 256;
     long long dims[5] = {d.K, d.N, bxm ? d.nbx : 1, bym ? d.nby : 1, 2};
