@@ -113,12 +113,19 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
 // q [n][D]; memory K / V blocks are contiguous per (utterance, head): kmem/vmem + ((u*H + h)*Tmax + t)*dk + d  (written once per
 // utterance by the K/V projection GEMMs and shared by the whole beam).  One block per (utterance, head): the K and V blocks are
 // streamed exactly once with coalesced 128-bit loads (LPR lanes per row, several rows per warp instruction, UN instructions in flight).
-template <int UN>
+// WC / DKC: compile-time beam size / head dim (0 = run-time values): the specialised instances have no predicates in the inner loops.
+template <int UN, int WC, int DKC>
 __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __restrict__ q, const float* __restrict__ kmem, const float* __restrict__ vmem,
-                                                           int Tmax, const int* __restrict__ lens, int W, int D, int H, int lpr /* pow2 >= dk/4 */,
+                                                           int Tmax, const int* __restrict__ lens, int W_rt, int D, int H, int lpr_rt /* pow2 >= dk/4 */,
                                                            float* __restrict__ ctx, long long ctx_plane) {
   extern __shared__ float sm[];  // q [W][dk] | scores [W][Tmax] (reused for the cross-warp PV reduction) | K tile [128][dk+4]
-  const int u = blockIdx.x / H, h = blockIdx.x % H, dk = D / H;
+  constexpr bool CT = (WC > 0);
+  constexpr int JMAX = CT ? (WC + 1) / 2 : 8;          // beam slots per half block
+  constexpr bool FULL = CT && (WC % 2 == 0);           // both halves own exactly JMAX slots
+  const int W = CT ? WC : W_rt;
+  const int dk = (DKC > 0) ? DKC : D / H;
+  const int lpr = (DKC == 64) ? 16 : lpr_rt;
+  const int u = blockIdx.x / H, h = blockIdx.x % H;
   const int T = lens[u];
   float* qs = sm;
   float* sc = qs + W * dk;
@@ -147,22 +154,22 @@ __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __res
       }
       __syncthreads();
       if (r < rows) {
-        float a[8];
+        float a[JMAX];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = 0.f;
+        for (int j = 0; j < JMAX; ++j) a[j] = 0.f;
         for (int d0 = 0; d0 < dk; d0 += 4) {
           const float4 k4 = *reinterpret_cast<const float4*>(kt + r * kst + d0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < JMAX; ++j) {
             const int w = w_lo + j;
-            if (w < w_hi) {
+            if (FULL || w < w_hi) {
               const float4 q4 = *reinterpret_cast<const float4*>(qs + w * dk + d0);
               a[j] = fmaf(q4.x, k4.x, a[j]); a[j] = fmaf(q4.y, k4.y, a[j]); a[j] = fmaf(q4.z, k4.z, a[j]); a[j] = fmaf(q4.w, k4.w, a[j]);
             }
           }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (w_lo + j < w_hi) sc[(w_lo + j) * Tmax + tb + r] = a[j] / rs;
+        for (int j = 0; j < JMAX; ++j) if (FULL || w_lo + j < w_hi) sc[(w_lo + j) * Tmax + tb + r] = a[j] / rs;
       }
       __syncthreads();
     }
@@ -184,9 +191,9 @@ __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __res
   // lane); each half streams V with coalesced 128-bit loads, UN row groups in flight per warp.
   const int hw = nwarp >> 1, hf = warp / hw, wh = warp % hw;
   const int w_lo = hf * ((W + 1) / 2), w_hi = min(W, w_lo + (W + 1) / 2);
-  float4 acc[8];
+  float4 acc[JMAX];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < JMAX; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t0 = wh * rpw * UN; t0 < T; t0 += hw * rpw * UN) {
     float4 vv[UN];
 #pragma unroll
@@ -198,8 +205,8 @@ __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __res
     for (int uu = 0; uu < UN; ++uu) {
       const int t = min(t0 + uu * rpw + rsub, T - 1);   // rows beyond T carry v = 0
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (w_lo + j < w_hi) {
+      for (int j = 0; j < JMAX; ++j) {
+        if (FULL || w_lo + j < w_hi) {
           const float pw = sc[(w_lo + j) * Tmax + t];
           acc[j].x = fmaf(pw, vv[uu].x, acc[j].x); acc[j].y = fmaf(pw, vv[uu].y, acc[j].y);
           acc[j].z = fmaf(pw, vv[uu].z, acc[j].z); acc[j].w = fmaf(pw, vv[uu].w, acc[j].w);
@@ -209,8 +216,8 @@ __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __res
   }
   // reduce over the rpw row groups of the warp (lanes with equal c4), then across the warps of the half through smem
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (w_lo + j < w_hi) {
+  for (int j = 0; j < JMAX; ++j) {
+    if (FULL || w_lo + j < w_hi) {
       for (int o = lpr; o < 32; o <<= 1) {
         acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, o); acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, o);
         acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, o); acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, o);
@@ -221,8 +228,8 @@ __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __res
   float* red = sc;
   if (rsub == 0 && col_ok) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (w_lo + j < w_hi) *reinterpret_cast<float4*>(red + ((long long)wh * W + w_lo + j) * dk + c4 * 4) = acc[j];
+    for (int j = 0; j < JMAX; ++j)
+      if (FULL || w_lo + j < w_hi) *reinterpret_cast<float4*>(red + ((long long)wh * W + w_lo + j) * dk + c4 * 4) = acc[j];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < W * dk; i += blockDim.x) {
@@ -603,14 +610,24 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
   const size_t red = (size_t)8 * W * dk, scs = ((size_t)W * Tmax + 3) & ~(size_t)3;
   const size_t smem = ((size_t)W * dk + (scs > red ? scs : red) + (size_t)128 * (dk + 4)) * sizeof(float);
   if (smem > 200 * 1024) { espb_set_error("dec_src_attn: beam*T too large for shared memory"); return ESPB_ERR_ARG; }
-  static size_t cur_max = 48 * 1024;
-  if (smem > cur_max) {
-    if (cudaFuncSetAttribute(dec_src_attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
+  using KernelFn = void (*)(const float*, const float*, const float*, int, const int*, int, int, int, int, float*, long long);
+  KernelFn fn = dec_src_attn_kernel<4, 0, 0>;
+  if (dk == 64) {
+    switch (W) {
+      case 4: fn = dec_src_attn_kernel<4, 4, 64>; break;
+      case 5: fn = dec_src_attn_kernel<4, 5, 64>; break;
+      case 8: fn = dec_src_attn_kernel<4, 8, 64>; break;
+      case 10: fn = dec_src_attn_kernel<4, 10, 64>; break;
+      case 16: fn = dec_src_attn_kernel<4, 16, 64>; break;
+      default: break;
+    }
+  }
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
       espb_set_error("dec_src_attn: cannot raise dynamic shared memory"); return ESPB_ERR_CUDA;
     }
-    cur_max = 200 * 1024;
   }
-  dec_src_attn_kernel<4><<<U * H, 256, smem, stream>>>(q, kmem, vmem, Tmax, lens, W, D, H, lpr, ctx, ctx_plane);
+  fn<<<U * H, 256, smem, stream>>>(q, kmem, vmem, Tmax, lens, W, D, H, lpr, ctx, ctx_plane);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

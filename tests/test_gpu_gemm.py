@@ -28,15 +28,15 @@ def _ref(a, b, bias=None, act=0, res=None, alpha=1.0):
     return v
 
 
-def _tol(mode, K, scale=1.0):
+def _tol(mode, K, scale=1.0, M=None):
     """SIMT: fp32 FFMA.  TC: fp32 accumulation inside the tensor core truncates (RZ), so the error of an O(1) output grows
     ~linearly with the number of accumulation steps (3*K/8); measured 9e-5 at K=2048."""
-    if mode == "tc":
+    if mode == "tc" or (mode == "tc2" and M is not None and M <= 1024):   # tc2 dispatches small-M problems to the 1-CTA tiles
         return scale * (2e-5 + 1.0e-7 * K)
     return scale * 2e-5   # simt (FFMA) and tc2 (chunked promotion: long accumulation chain in fp32 registers)
 
 
-SHAPES = [(128, 64, 32), (128, 256, 64), (200, 130, 96), (640, 512, 512), (937, 512, 2048), (22, 50, 64), (300, 5000, 64),
+SHAPES = [(2000, 512, 2048), (1500, 1536, 512), (128, 64, 32), (128, 256, 64), (200, 130, 96), (640, 512, 512), (937, 512, 2048), (22, 50, 64), (300, 5000, 64),
           (1000, 1536, 512), (129, 65, 33 * 4)]
 
 
@@ -55,7 +55,7 @@ def test_linear_plain(mode, M, N, K):
     ref = _ref(a, b, bias)
     err = (out.double() - ref).abs().max().item()
     print(f"[{mode}] M{M} N{N} K{K} max abs err {err:.3e}")
-    assert err < _tol(mode, K), f"{mode} M{M} N{N} K{K} max abs err {err}"
+    assert err < _tol(mode, K, M=M), f"{mode} M{M} N{N} K{K} max abs err {err}"
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -70,16 +70,16 @@ def test_linear_epilogues(mode):
     outs = torch.zeros(2, M, N, device="cuda")
     ops.linear(_split(a), _split(b), outs, bias=bias, act=ops.ACT_SWISH, split_out=True, force=mode)
     ref = _ref(a, b, bias, act=2)
-    assert ((outs[0].double() + outs[1].double()) - ref).abs().max().item() < _tol(mode, K)
+    assert ((outs[0].double() + outs[1].double()) - ref).abs().max().item() < _tol(mode, K, M=M)
     assert (outs[0].view(torch.int32) & 0x1FFF).abs().max().item() == 0  # hi plane is exactly tf32
     # relu
     out = torch.zeros(M, N, device="cuda")
     ops.linear(_split(a), _split(b), out, bias=bias, act=ops.ACT_RELU, force=mode)
-    assert (out.double() - _ref(a, b, bias, act=1)).abs().max().item() < _tol(mode, K)
+    assert (out.double() - _ref(a, b, bias, act=1)).abs().max().item() < _tol(mode, K, M=M)
     # in-place residual with alpha
     x = res.clone()
     ops.linear(_split(a), _split(b), x, bias=bias, residual=x, alpha=0.5, force=mode)
-    assert (x.double() - _ref(a, b, bias, res=res, alpha=0.5)).abs().max().item() < _tol(mode, K)
+    assert (x.double() - _ref(a, b, bias, res=res, alpha=0.5)).abs().max().item() < _tol(mode, K, M=M)
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -100,7 +100,7 @@ def test_batched_strided_attention_shapes(mode):
     qh = q.view(Bn, T, H, dk).permute(0, 2, 1, 3).double()
     kh = qkv[:, D:2 * D].reshape(Bn, T, H, dk).permute(0, 2, 1, 3).double()
     ref = qh @ kh.transpose(-1, -2)
-    assert (ac[..., :T].double() - ref).abs().max().item() < _tol(mode, dk, 4)
+    assert (ac[..., :T].double() - ref).abs().max().item() < _tol(mode, dk, 4, M=T)
     # shared B across batch-y (positional matrix), output pitch Rp
     R, L, Rp = 2 * T - 1, 2, 156
     p_all = torch.randn(R, L * D, device="cuda")
@@ -109,7 +109,7 @@ def test_batched_strided_attention_shapes(mode):
              sc=(T * Rp, H * T * Rp), b_off=1 * D, force=mode)
     ph = p_all[:, D:2 * D].reshape(R, H, dk).permute(1, 0, 2).double()
     ref = qh @ ph.transpose(-1, -2).unsqueeze(0)
-    assert (bd[..., :R].double() - ref).abs().max().item() < _tol(mode, dk, 4)
+    assert (bd[..., :R].double() - ref).abs().max().item() < _tol(mode, dk, 4, M=T)
     # P @ V with K = T (not a multiple of 32) and transposed V, output scattered back to [M][D] (split)
     probs = torch.rand(Bn, H, T, Tp, device="cuda")
     probs[..., T:] = 0
@@ -118,7 +118,7 @@ def test_batched_strided_attention_shapes(mode):
     ops.gemm(T, dk, T, _split(probs), Bn * H * T * Tp, Tp, _split(vt), Bn * H * dk * Tp, Tp, ctx, D, c_plane=M * D, split_out=True,
              nbx=H, nby=Bn, sa=(T * Tp, H * T * Tp), sb=(dk * Tp, H * dk * Tp), sc=(dk, T * D), force=mode)
     ref = (probs[..., :T].double() @ vt[..., :T].double().transpose(-1, -2)).permute(0, 2, 1, 3).reshape(M, D)
-    assert ((ctx[0].double() + ctx[1].double()) - ref).abs().max().item() < _tol(mode, T, 4)
+    assert ((ctx[0].double() + ctx[1].double()) - ref).abs().max().item() < _tol(mode, T, 4, M=T)
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -162,4 +162,4 @@ def test_conv2_implicit_gemm_and_outer_k(mode):
     ops.gemm(T2, D, F2 * C, c2, Bn * F2 * T2 * C, C, wop, D * F2 * C, F2 * C, x, D, bias=bo, alpha=math.sqrt(D), nbx=1, nby=Bn,
              sa=(T2 * C, F2 * T2 * C), sc=(0, T2 * D), kob=C // 32, force=mode)
     ref = (x2.transpose(1, 2).reshape(Bn, T2, C * F2) @ wo.double().t() + bo.double()) * math.sqrt(D)
-    assert (x.view(Bn, T2, D).double() - ref).abs().max().item() < _tol(mode, F2 * C, 10)
+    assert (x.view(Bn, T2, D).double() - ref).abs().max().item() < _tol(mode, F2 * C, 10, M=T2)
