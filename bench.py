@@ -329,13 +329,13 @@ def run_b200(args, rank, local_rank, world):
         "data": "synthetic", "rtf": (dev_ms / 1000.0) / (utts * secs),
         "config": {"workload": args.workload, "global_batch": world * batch, "utt_seconds": secs, "beam": beam, "ctc_weight": ctcw,
                    "maxlenratio": mlr, "vocab": cfg["vocab"], "parallelism": f"utterance-sharded x{world}", "l2": "flushed between steps (256 MiB write)",
-                   "gemm": "tcgen05 kind::tf32 x3 (error-compensated fp32)", "wall_s_timed_region": wall},
+                   "gemm": "tcgen05 kind::tf32 x3 (error-compensated fp32), mode " + ops.gemm_mode(), "wall_s_timed_region": wall},
         "e2e": {"value": e2e, "unit": "utterances/s", "h2d_bytes_per_step": batch * nsamp * 4,
                 "d2h_bytes_per_step": int(2 * 4 * 64 * batch * beam + 6 * 4 * batch * beam * 64), "ms_per_step": e2e_ms / args.steps,
                 "hyp_tokens_last_step": n_hyp_tokens},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tf32x3_kernel (all launches of one step)", "achieved": ach, "peak": peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tf32x3_2cta_kernel / gemm_tf32x3_kernel (all tensor-core GEMM launches of one step)", "achieved": ach, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
                      "launches": len(prof), "gemm_ms_per_step": g_ms,
                      "note": "algorithmic FLOPs (2MNK); each is executed as 3 tf32 MMAs at half the bf16 rate, so 1/6 of the bf16 peak is the ceiling of this formulation"},

@@ -707,7 +707,7 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
   if (rc != ESPB_OK) return rc;
   const int bxm = d.sb_x != 0 ? 1 : 0, bym = d.sb_y != 0 ? 1 : 0;
   const long long tiles_m = (d.M + BM - 1) / BM, nb = (long long)d.nbx * d.nby;
-  if (version == 2 && d.M > 1024) {   // small-M (decode) problems are latency-bound: the 128x64 1-CTA tiles spread them over more SMs
+  if (version == 2 && (long long)d.M * d.nbx * d.nby > 1024) {   // tiny (decode-step) problems are latency-bound: 128x64 1-CTA tiles spread them over more SMs
     // CTA-pair kernel: 256 x BN tiles; B box = BN/2 rows per CTA
     const int bn = (d.N <= 128) ? 128 : 256;
     long long dims[5] = {d.K, d.N, bxm ? d.nbx : 1, bym ? d.nby : 1, 2};

@@ -14,7 +14,7 @@ ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2
 
 # GEMM kernel: "tc" = tcgen05 1-CTA, "tc2" = tcgen05 CTA pair + chunked fp32 promotion, "simt" = FFMA (bring-up / A-B checks);
 # shapes TMA cannot address always use SIMT.
-_GEMM_MODE = os.environ.get("ESPNET_B200_GEMM", "tc")
+_GEMM_MODE = os.environ.get("ESPNET_B200_GEMM", "tc2")
 launch_counter = [0]
 gemm_profile = None  # set to a list to record (algorithmic flops, start event, end event) per tensor-core GEMM launch
 
