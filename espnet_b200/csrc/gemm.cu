@@ -286,11 +286,13 @@ __device__ __forceinline__ void mma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, ui
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// relaxed: the barrier only orders TMEM reads (already fenced by tcgen05.wait::ld / fence::before_thread_sync); a release fence here
+// would make every chunk hand-over wait for the epilogue's outstanding global stores.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t target_rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(local_bar), "r"(target_rank)
       : "memory");
 }
