@@ -229,7 +229,9 @@ class ConformerEncoder(torch.nn.Module):
         olens = torch.div(torch.div(ilens - 1, 2, rounding_mode="trunc") - 1, 2, rounding_mode="trunc")
         lens32 = olens.to(device=dev, dtype=torch.int32).contiguous()
         M = B * T
-        Tp, Rp = (T + 3) // 4 * 4, (2 * T - 1 + 3) // 4 * 4
+        # row pitches of the score / probability matrices: multiples of 32 floats so that every 128-byte store segment of the GEMM
+        # epilogues is a whole cache line (partial-sector writes cost a DRAM read-modify-write)
+        Tp, Rp = (T + 31) // 32 * 32, (2 * T - 1 + 31) // 32 * 32
 
         # ---- Conv2dSubsampling (subsampling.py:432-474)
         c1 = self._buf("c1", (B, 8, F1h, T1h, C), zero=True)
