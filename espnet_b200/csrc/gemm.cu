@@ -30,18 +30,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: the warp sleeps in hardware instead of spinning through the issue slots the epilogue warps need.
   uint32_t done = 0;
-  long long t0 = clock64();
-  while (true) {
+  for (int spin = 0; ; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s watchdog: fail loudly instead of hanging the GPU
+    if (spin > (1 << 22)) __trap();  // watchdog: fail loudly instead of hanging the GPU
   }
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
@@ -120,6 +120,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int bx = blockIdx.z % p.nbx, by = blockIdx.z / p.nbx;
   const int num_kb = (p.K + BK - 1) / BK;
+  if (p.band_t > 0 && ((n0 + BN - 1 < p.band_t - 1 - (m0 + BM - 1)) || (n0 > 2 * p.band_t - 2 - m0))) return;   // tile outside the rel-pos band
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
@@ -297,8 +298,15 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
       : "memory");
 }
 
+// rel-pos band (EspbGemmDesc::band_t): a tile of rows [m0, m0+bm) x columns [n0, n0+bn) is needed iff it intersects
+// { (m, n) : T-1-m <= n <= 2T-2-m }.
+__device__ __forceinline__ bool band_skip(int T, int m0, int bm, int n0, int bn) {
+  if (T <= 0) return false;
+  return (n0 + bn - 1 < T - 1 - (m0 + bm - 1)) || (n0 > 2 * T - 2 - m0);
+}
+
 template <int BN, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
 gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym, int axm, int aym) {
   constexpr int BH = BN / 2;                      // B rows staged by each CTA
   constexpr int B_TILE_BYTES = BH * 128;
@@ -351,6 +359,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int nt = (int)(tile % tiles_n);
         const int mt = (int)((tile / tiles_n) % tiles_m);
         const int z = (int)(tile / ((long long)tiles_m * tiles_n));
+        if (band_skip(p.band_t, mt * 256, 256, nt * BN, BN)) continue;
         const int bx = z % p.nbx, by = z / p.nbx;
         const int m0 = mt * 256 + (int)rank * 128, nb = nt * BN + (int)rank * BH;
         for (int kb = 0; kb < num_kb; ++kb, ++g) {
@@ -382,6 +391,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       long long g = 0, cg = 0;                                // global k-block / chunk counters
       for (long long tile = pair; tile < total_tiles; tile += num_pairs) {
+        if (band_skip(p.band_t, (int)((tile / tiles_n) % tiles_m) * 256, 256, (int)(tile % tiles_n) * BN, BN)) continue;
         for (int c = 0; c < num_chunks; ++c, ++cg) {
           const int b = (int)(cg & 1);
           mbar_wait(tempty_bar + 8 * b, (uint32_t)(((cg >> 1) & 1) ^ 1));   // both CTAs' epilogues have drained this accumulator buffer
@@ -417,6 +427,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int nt = (int)(tile % tiles_n);
       const int mt = (int)((tile / tiles_n) % tiles_m);
       const int z = (int)(tile / ((long long)tiles_m * tiles_n));
+      if (band_skip(p.band_t, mt * 256, 256, nt * BN, BN)) continue;
       const int bx = z % p.nbx, by = z / p.nbx;
       const int m0 = mt * 256 + (int)rank * 128, n0 = nt * BN;
       float acc[CW];
@@ -451,63 +462,72 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                           (!p.bias || ((((long long)bx * p.sbias_x) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
       const int row0 = m0 + q * 32;
       const int rsub = lane >> 3, c4 = (lane & 7) * 4;     // read mapping: 4 rows x 8 float4 per warp access
+      const int rows_left = p.M - row0 - rsub;             // this lane's rows row0 + rsub + 4k are valid while 4k < rows_left
+      const long long ldc = ea.ldc, ldr = ea.ldr, cpl = ea.c_plane;
+      const int act = ea.act, Ncols = p.N;
+      const float alpha = ea.alpha;
+      const bool split = ea.split_out != 0, has_r = ea.R != nullptr;
+      float* const crow0 = ea.C + (long long)(row0 + rsub) * ldc;
+      const float* const rrow0 = has_r ? ea.R + (long long)(row0 + rsub) * ldr : nullptr;
+      float* const wrow = xp + (lane & 15) * 36;
+      const float* const rbase = xp + rsub * 36 + c4;
 #pragma unroll
       for (int j = 0; j < CW / 32; ++j) {
         const int colb = n0 + half * CW + j * 32;
-        if (row0 >= p.M || colb >= p.N) continue;            // warp-uniform: block entirely outside the matrix
+        if (row0 >= p.M || colb >= Ncols) continue;          // warp-uniform: block entirely outside the matrix
         const int col = colb + c4;
-        const bool full4 = vec_ok && (col + 3 < p.N);
+        const bool full4 = vec_ok && (col + 3 < Ncols);
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ea.bias && full4) b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col));
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {                     // rows hh*16 .. hh*16+15 of the block
           __syncwarp();
           if ((lane >> 4) == hh) {
-            float* w = xp + (lane & 15) * 36;
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(w + i) = make_float4(acc[j * 32 + i], acc[j * 32 + i + 1], acc[j * 32 + i + 2], acc[j * 32 + i + 3]);
+              *reinterpret_cast<float4*>(wrow + i) = make_float4(acc[j * 32 + i], acc[j * 32 + i + 1], acc[j * 32 + i + 2], acc[j * 32 + i + 3]);
           }
           __syncwarp();
           float4 rv[4];
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            const long long row = row0 + hh * 16 + it * 4 + rsub;
-            rv[it] = (ea.R && full4 && row < p.M) ? *reinterpret_cast<const float4*>(ea.R + row * ea.ldr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int rl = hh * 16 + it * 4;
+            rv[it] = (has_r && full4 && rl < rows_left) ? *reinterpret_cast<const float4*>(rrow0 + (long long)rl * ldr + col)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            const int rl = it * 4 + rsub;
-            const long long row = row0 + hh * 16 + rl;
-            if (row >= p.M) continue;
-            const float4 v = *reinterpret_cast<const float4*>(xp + rl * 36 + c4);
-            float* cp = ea.C + row * ea.ldc + col;
+            const int rl = hh * 16 + it * 4;
+            if (rl >= rows_left) continue;
+            const float4 v = *reinterpret_cast<const float4*>(rbase + it * 4 * 36);
+            float* cp = crow0 + (long long)rl * ldc + col;
             if (full4) {
               float t[4] = {v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w};
               const float rr4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float x = t[i];
-                if (ea.act == espb::ACT_RELU) x = fmaxf(x, 0.f);
-                else if (ea.act == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
-                t[i] = fmaf(ea.alpha, x, rr4[i]);
+                if (act == espb::ACT_RELU) x = fmaxf(x, 0.f);
+                else if (act == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
+                t[i] = fmaf(alpha, x, rr4[i]);
               }
-              if (ea.split_out) {
+              if (split) {
                 float4 h, l;
                 h.x = espb::tf32_hi(t[0]); h.y = espb::tf32_hi(t[1]); h.z = espb::tf32_hi(t[2]); h.w = espb::tf32_hi(t[3]);
                 l.x = espb::tf32_lo(t[0], h.x); l.y = espb::tf32_lo(t[1], h.y); l.z = espb::tf32_lo(t[2], h.z); l.w = espb::tf32_lo(t[3], h.w);
                 *reinterpret_cast<float4*>(cp) = h;
-                *reinterpret_cast<float4*>(cp + ea.c_plane) = l;
+                *reinterpret_cast<float4*>(cp + cpl) = l;
               } else {
                 *reinterpret_cast<float4*>(cp) = make_float4(t[0], t[1], t[2], t[3]);
               }
             } else {
               const float vv[4] = {v.x, v.y, v.z, v.w};
+              const long long row = row0 + rsub + rl;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                if (col + i < p.N) {
+                if (col + i < Ncols) {
                   const float tt = epi_value(ea, vv[i], row, col + i);
-                  if (ea.split_out) { const float hh2 = espb::tf32_hi(tt); cp[i] = hh2; cp[ea.c_plane + i] = espb::tf32_lo(tt, hh2); }
+                  if (split) { const float hh2 = espb::tf32_hi(tt); cp[i] = hh2; cp[cpl + i] = espb::tf32_lo(tt, hh2); }
                   else cp[i] = tt;
                 }
               }
@@ -555,6 +575,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(EspbGemmDesc p) {
   const int bx = blockIdx.z % p.nbx, by = blockIdx.z / p.nbx;
   const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  if (p.band_t > 0 && ((n0 + 63 < p.band_t - 1 - (m0 + 63)) || (n0 > 2 * p.band_t - 2 - m0))) return;
   float acc[4][4] = {};
   for (int k0 = 0; k0 < p.K; k0 += 16) {
     for (int i = threadIdx.x; i < 64 * 16; i += 256) {

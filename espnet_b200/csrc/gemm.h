@@ -25,6 +25,7 @@ struct EspbGemmDesc {
   float alpha;          // out = R + alpha * act(acc + bias)   (R absent: alpha * act(...))
   int act;              // espb::ACT_*
   int cv_t1h, cv_f1h, cv_cin;  // mode 1: conv1-output half extents and channel count
+  int band_t;           // > 0: only columns n with band_t-1-m <= n <= 2*band_t-2-m are ever read (rel-pos shift): tiles outside are skipped
 };
 
 int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version);  // tcgen05 (1: 1-CTA, 2: CTA pair + chunked promotion)

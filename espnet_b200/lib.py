@@ -27,7 +27,7 @@ class GemmDesc(Structure):
         ("C", c_void_p), ("c_plane", c_longlong), ("ldc", c_longlong), ("sc_x", c_longlong), ("sc_y", c_longlong),
         ("split_out", c_int), ("bias", c_void_p), ("sbias_x", c_longlong),
         ("R", c_void_p), ("ldr", c_longlong), ("sr_x", c_longlong), ("sr_y", c_longlong),
-        ("alpha", c_float), ("act", c_int), ("cv_t1h", c_int), ("cv_f1h", c_int), ("cv_cin", c_int),
+        ("alpha", c_float), ("act", c_int), ("cv_t1h", c_int), ("cv_f1h", c_int), ("cv_cin", c_int), ("band_t", c_int),
     ]
 
 

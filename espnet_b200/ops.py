@@ -48,7 +48,7 @@ def split_from(x):
 
 def gemm(M, N, K, A, a_plane, lda, B, b_plane, ldb, C, ldc, *, c_plane=0, split_out=False, bias=None, R=None, ldr=0,
          alpha=1.0, act=ACT_NONE, nbx=1, nby=1, sa=(0, 0), sb=(0, 0), sc=(0, 0), sr=(0, 0), kob=0, a_mode=0, conv=(0, 0, 0),
-         a_off=0, b_off=0, c_off=0, r_off=0, sbias_x=0, bias_off=0, force=None):
+         a_off=0, b_off=0, c_off=0, r_off=0, sbias_x=0, bias_off=0, band_t=0, force=None):
     """Raw strided GEMM launch; A/B/C/R are tensors (base pointers), *_off element offsets."""
     d = GemmDesc()
     d.M, d.N, d.K, d.nbx, d.nby, d.a_mode, d.kob = M, N, K, nbx, nby, a_mode, kob
@@ -65,6 +65,7 @@ def gemm(M, N, K, A, a_plane, lda, B, b_plane, ldb, C, ldc, *, c_plane=0, split_
     d.ldr, d.sr_x, d.sr_y = ldr, sr[0], sr[1]
     d.alpha, d.act = float(alpha), act
     d.cv_t1h, d.cv_f1h, d.cv_cin = conv
+    d.band_t = band_t
     mode = force or _GEMM_MODE
     use_tc = {"tc": 1, "tc2": 2}.get(mode, 0)
     if use_tc:
