@@ -306,7 +306,7 @@ __device__ __forceinline__ bool band_skip(int T, int m0, int bm, int n0, int bn)
 }
 
 template <int BN, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(192)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
 gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym, int axm, int aym) {
   constexpr int BH = BN / 2;                      // B rows staged by each CTA
   constexpr int B_TILE_BYTES = BH * 128;
