@@ -298,69 +298,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
       : "memory");
 }
 
-// Epilogue store of one 16-row x 32-column half block that a warp has just transposed into its smem buffer `xp` ([16][36] floats).
-// Kept out of line: the caller is unrolled 8x per tile (static accumulator indices) and inlining this body made the kernel ~250 KB of
-// SASS, i.e. instruction-cache bound.
-struct EpiStore {
-  EpiArgs ea;
-  const float* xp_read;   // xp + rsub*36 + c4
-  float* crow0;           // C + (row0 + rsub) * ldc
-  const float* rrow0;     // R + (row0 + rsub) * ldr (or null)
-  int rows_left, Ncols, row_first;   // valid rows for this lane (stride 4), matrix columns, row0 + rsub
-  bool vec_ok;
-};
-
-__device__ __noinline__ void epi_store_half_block(const EpiStore& st, int col, int rl0) {
-  const EpiArgs& ea = st.ea;
-  const bool full4 = st.vec_ok && (col + 3 < st.Ncols);
-  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ea.bias && full4) b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col));
-  float4 rv[4];
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int rl = rl0 + it * 4;
-    rv[it] = (st.rrow0 && full4 && rl < st.rows_left) ? *reinterpret_cast<const float4*>(st.rrow0 + (long long)rl * ea.ldr + col)
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int rl = rl0 + it * 4;
-    if (rl >= st.rows_left) continue;
-    const float4 v = *reinterpret_cast<const float4*>(st.xp_read + it * 4 * 36);
-    float* cp = st.crow0 + (long long)rl * ea.ldc + col;
-    if (full4) {
-      float t[4] = {v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w};
-      const float rr4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float x = t[i];
-        if (ea.act == espb::ACT_RELU) x = fmaxf(x, 0.f);
-        else if (ea.act == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
-        t[i] = fmaf(ea.alpha, x, rr4[i]);
-      }
-      if (ea.split_out) {
-        float4 h, l;
-        h.x = espb::tf32_hi(t[0]); h.y = espb::tf32_hi(t[1]); h.z = espb::tf32_hi(t[2]); h.w = espb::tf32_hi(t[3]);
-        l.x = espb::tf32_lo(t[0], h.x); l.y = espb::tf32_lo(t[1], h.y); l.z = espb::tf32_lo(t[2], h.z); l.w = espb::tf32_lo(t[3], h.w);
-        *reinterpret_cast<float4*>(cp) = h;
-        *reinterpret_cast<float4*>(cp + ea.c_plane) = l;
-      } else {
-        *reinterpret_cast<float4*>(cp) = make_float4(t[0], t[1], t[2], t[3]);
-      }
-    } else {
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-      const long long row = st.row_first + rl;
-      for (int i = 0; i < 4; ++i) {
-        if (col + i < st.Ncols) {
-          const float tt = epi_value(ea, vv[i], row, col + i);
-          if (ea.split_out) { const float hh2 = espb::tf32_hi(tt); cp[i] = hh2; cp[ea.c_plane + i] = espb::tf32_lo(tt, hh2); }
-          else cp[i] = tt;
-        }
-      }
-    }
-  }
-}
-
 // rel-pos band (EspbGemmDesc::band_t): a tile of rows [m0, m0+bm) x columns [n0, n0+bn) is needed iff it intersects
 // { (m, n) : T-1-m <= n <= 2T-2-m }.
 __device__ __forceinline__ bool band_skip(int T, int m0, int bm, int n0, int bn) {
@@ -525,16 +462,23 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                           (!p.bias || ((((long long)bx * p.sbias_x) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
       const int row0 = m0 + q * 32;
       const int rsub = lane >> 3, c4 = (lane & 7) * 4;     // read mapping: 4 rows x 8 float4 per warp access
-      EpiStore st;
-      st.ea = ea; st.xp_read = xp + rsub * 36 + c4;
-      st.crow0 = ea.C + (long long)(row0 + rsub) * ea.ldc;
-      st.rrow0 = ea.R ? ea.R + (long long)(row0 + rsub) * ea.ldr : nullptr;
-      st.rows_left = p.M - row0 - rsub; st.Ncols = p.N; st.row_first = row0 + rsub; st.vec_ok = vec_ok;
+      const int rows_left = p.M - row0 - rsub;             // this lane's rows row0 + rsub + 4k are valid while 4k < rows_left
+      const long long ldc = ea.ldc, ldr = ea.ldr, cpl = ea.c_plane;
+      const int act = ea.act, Ncols = p.N;
+      const float alpha = ea.alpha;
+      const bool split = ea.split_out != 0, has_r = ea.R != nullptr;
+      float* const crow0 = ea.C + (long long)(row0 + rsub) * ldc;
+      const float* const rrow0 = has_r ? ea.R + (long long)(row0 + rsub) * ldr : nullptr;
       float* const wrow = xp + (lane & 15) * 36;
+      const float* const rbase = xp + rsub * 36 + c4;
 #pragma unroll
       for (int j = 0; j < CW / 32; ++j) {
         const int colb = n0 + half * CW + j * 32;
-        if (row0 >= p.M || colb >= p.N) continue;            // warp-uniform: block entirely outside the matrix
+        if (row0 >= p.M || colb >= Ncols) continue;          // warp-uniform: block entirely outside the matrix
+        const int col = colb + c4;
+        const bool full4 = vec_ok && (col + 3 < Ncols);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ea.bias && full4) b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col));
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {                     // rows hh*16 .. hh*16+15 of the block
           __syncwarp();
@@ -544,7 +488,51 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
               *reinterpret_cast<float4*>(wrow + i) = make_float4(acc[j * 32 + i], acc[j * 32 + i + 1], acc[j * 32 + i + 2], acc[j * 32 + i + 3]);
           }
           __syncwarp();
-          epi_store_half_block(st, colb + c4, hh * 16);
+          float4 rv[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rl = hh * 16 + it * 4;
+            rv[it] = (has_r && full4 && rl < rows_left) ? *reinterpret_cast<const float4*>(rrow0 + (long long)rl * ldr + col)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rl = hh * 16 + it * 4;
+            if (rl >= rows_left) continue;
+            const float4 v = *reinterpret_cast<const float4*>(rbase + it * 4 * 36);
+            float* cp = crow0 + (long long)rl * ldc + col;
+            if (full4) {
+              float t[4] = {v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w};
+              const float rr4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float x = t[i];
+                if (act == espb::ACT_RELU) x = fmaxf(x, 0.f);
+                else if (act == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
+                t[i] = fmaf(alpha, x, rr4[i]);
+              }
+              if (split) {
+                float4 h, l;
+                h.x = espb::tf32_hi(t[0]); h.y = espb::tf32_hi(t[1]); h.z = espb::tf32_hi(t[2]); h.w = espb::tf32_hi(t[3]);
+                l.x = espb::tf32_lo(t[0], h.x); l.y = espb::tf32_lo(t[1], h.y); l.z = espb::tf32_lo(t[2], h.z); l.w = espb::tf32_lo(t[3], h.w);
+                *reinterpret_cast<float4*>(cp) = h;
+                *reinterpret_cast<float4*>(cp + cpl) = l;
+              } else {
+                *reinterpret_cast<float4*>(cp) = make_float4(t[0], t[1], t[2], t[3]);
+              }
+            } else {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+              const long long row = row0 + rsub + rl;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (col + i < Ncols) {
+                  const float tt = epi_value(ea, vv[i], row, col + i);
+                  if (split) { const float hh2 = espb::tf32_hi(tt); cp[i] = hh2; cp[cpl + i] = espb::tf32_lo(tt, hh2); }
+                  else cp[i] = tt;
+                }
+              }
+            }
+          }
         }
       }
     }
