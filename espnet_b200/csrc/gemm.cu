@@ -305,7 +305,8 @@ __device__ __forceinline__ bool band_skip(int T, int m0, int bm, int n0, int bn)
   return (n0 + bn - 1 < T - 1 - (m0 + bm - 1)) || (n0 > 2 * T - 2 - m0);
 }
 
-template <int BN, int STAGES>
+// ACT / SPLIT are compile-time so that the 128-bit epilogue path carries no per-element branches.
+template <int BN, int STAGES, int ACT, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
 gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym, int axm, int aym) {
   constexpr int BH = BN / 2;                      // B rows staged by each CTA
@@ -464,9 +465,9 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int rsub = lane >> 3, c4 = (lane & 7) * 4;     // read mapping: 4 rows x 8 float4 per warp access
       const int rows_left = p.M - row0 - rsub;             // this lane's rows row0 + rsub + 4k are valid while 4k < rows_left
       const long long ldc = ea.ldc, ldr = ea.ldr, cpl = ea.c_plane;
-      const int act = ea.act, Ncols = p.N;
+      const int Ncols = p.N;
       const float alpha = ea.alpha;
-      const bool split = ea.split_out != 0, has_r = ea.R != nullptr;
+      const bool split = SPLIT, has_r = ea.R != nullptr;
       float* const crow0 = ea.C + (long long)(row0 + rsub) * ldc;
       const float* const rrow0 = has_r ? ea.R + (long long)(row0 + rsub) * ldr : nullptr;
       float* const wrow = xp + (lane & 15) * 36;
@@ -507,11 +508,11 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float x = t[i];
-                if (act == espb::ACT_RELU) x = fmaxf(x, 0.f);
-                else if (act == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
+                if (ACT == espb::ACT_RELU) x = fmaxf(x, 0.f);
+                else if (ACT == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
                 t[i] = fmaf(alpha, x, rr4[i]);
               }
-              if (split) {
+              if (SPLIT) {
                 float4 h, l;
                 h.x = espb::tf32_hi(t[0]); h.y = espb::tf32_hi(t[1]); h.z = espb::tf32_hi(t[2]); h.w = espb::tf32_hi(t[3]);
                 l.x = espb::tf32_lo(t[0], h.x); l.y = espb::tf32_lo(t[1], h.y); l.z = espb::tf32_lo(t[2], h.z); l.w = espb::tf32_lo(t[3], h.w);
@@ -681,14 +682,14 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc
   return ESPB_OK;
 }
 
-template <int BN, int STAGES>
-int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
+template <int BN, int STAGES, int ACT, bool SPLIT>
+int launch_tc2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
   constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * (BN / 2) * 128) + 8 * 16 * 36 * 4 + 1024 + 16 * STAGES + 64;
   static_assert(smem <= 232448, "dynamic shared memory budget exceeded");
   static bool attr_set = false;
   static int num_sms = 0;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tf32x3_2cta_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tf32x3_2cta_kernel<BN, STAGES, ACT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       espb_set_error("cudaFuncSetAttribute(max dynamic smem) failed");
       return ESPB_ERR_CUDA;
     }
@@ -700,9 +701,23 @@ int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDes
   const long long tiles = (long long)((d.M + 255) / 256) * ((d.N + BN - 1) / BN) * d.nbx * d.nby;
   const long long pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;   // persistent: one CTA pair per SM pair
   dim3 grid((unsigned)(2 * pairs), 1, 1);
-  gemm_tf32x3_2cta_kernel<BN, STAGES><<<grid, V2_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
+  gemm_tf32x3_2cta_kernel<BN, STAGES, ACT, SPLIT><<<grid, V2_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
+}
+
+template <int BN, int STAGES>
+int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
+  const int v = d.act * 2 + (d.split_out ? 1 : 0);
+  switch (v) {
+    case 0: return launch_tc2_v<BN, STAGES, espb::ACT_NONE, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 1: return launch_tc2_v<BN, STAGES, espb::ACT_NONE, true>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 2: return launch_tc2_v<BN, STAGES, espb::ACT_RELU, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 3: return launch_tc2_v<BN, STAGES, espb::ACT_RELU, true>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 4: return launch_tc2_v<BN, STAGES, espb::ACT_SWISH, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 5: return launch_tc2_v<BN, STAGES, espb::ACT_SWISH, true>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    default: espb_set_error("gemm: unknown activation"); return ESPB_ERR_ARG;
+  }
 }
 
 }  // namespace
