@@ -305,6 +305,15 @@ __device__ __forceinline__ bool band_skip(int T, int m0, int bm, int n0, int bn)
   return (n0 + bn - 1 < T - 1 - (m0 + bm - 1)) || (n0 > 2 * T - 2 - m0);
 }
 
+// Dynamic read of a register array (cold scalar path only): unrolled compare/select keeps `acc` in registers.
+template <int N>
+__device__ __forceinline__ float acc_at(const float (&acc)[N], int idx) {
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r = (i == idx) ? acc[i] : r;
+  return r;
+}
+
 // ACT / SPLIT are compile-time so that the 128-bit epilogue path carries no per-element branches.
 template <int BN, int STAGES, int ACT, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
@@ -472,64 +481,94 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const float* const rrow0 = has_r ? ea.R + (long long)(row0 + rsub) * ldr : nullptr;
       float* const wrow = xp + (lane & 15) * 36;
       const float* const rbase = xp + rsub * 36 + c4;
+      // 128-bit path: row / column predicates only (warp-uniform block skips), pointers advanced incrementally
+      if (vec_ok) {
+        const bool has_b = ea.bias != nullptr;
 #pragma unroll
-      for (int j = 0; j < CW / 32; ++j) {
-        const int colb = n0 + half * CW + j * 32;
-        if (row0 >= p.M || colb >= Ncols) continue;          // warp-uniform: block entirely outside the matrix
-        const int col = colb + c4;
-        const bool full4 = vec_ok && (col + 3 < Ncols);
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ea.bias && full4) b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col));
+        for (int j = 0; j < CW / 32; ++j) {
+          const int colb = n0 + half * CW + j * 32;
+          if (row0 >= p.M || colb >= Ncols) continue;          // warp-uniform: block entirely outside the matrix
+          const int col = colb + c4;
+          const bool c_full = col + 3 < Ncols, c_part = !c_full && col < Ncols;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_b && c_full) b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col));
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {                     // rows hh*16 .. hh*16+15 of the block
-          __syncwarp();
-          if ((lane >> 4) == hh) {
+          for (int hh = 0; hh < 2; ++hh) {
+            __syncwarp();
+            if ((lane >> 4) == hh) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(wrow + i) = make_float4(acc[j * 32 + i], acc[j * 32 + i + 1], acc[j * 32 + i + 2], acc[j * 32 + i + 3]);
-          }
-          __syncwarp();
-          float4 rv[4];
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(wrow + i) = make_float4(acc[j * 32 + i], acc[j * 32 + i + 1], acc[j * 32 + i + 2], acc[j * 32 + i + 3]);
+            }
+            __syncwarp();
+            float* cp = crow0 + (long long)(hh * 16) * ldc + col;
+            float4 rv[4];
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rl = hh * 16 + it * 4;
-            rv[it] = (has_r && full4 && rl < rows_left) ? *reinterpret_cast<const float4*>(rrow0 + (long long)rl * ldr + col)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+            for (int it = 0; it < 4; ++it) {
+              rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_r && c_full && hh * 16 + it * 4 < rows_left)
+                rv[it] = *reinterpret_cast<const float4*>(rrow0 + (long long)(hh * 16 + it * 4) * ldr + col);
+            }
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rl = hh * 16 + it * 4;
-            if (rl >= rows_left) continue;
-            const float4 v = *reinterpret_cast<const float4*>(rbase + it * 4 * 36);
-            float* cp = crow0 + (long long)rl * ldc + col;
-            if (full4) {
-              float t[4] = {v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w};
-              const float rr4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
+            for (int it = 0; it < 4; ++it) {
+              const int rl = hh * 16 + it * 4;
+              if (rl >= rows_left) continue;
+              const float4 v = *reinterpret_cast<const float4*>(rbase + it * 4 * 36);
+              float* cpi = cp + (long long)(it * 4) * ldc;
+              if (c_full) {
+                float t[4] = {v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w};
+                const float rr4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float x = t[i];
-                if (ACT == espb::ACT_RELU) x = fmaxf(x, 0.f);
-                else if (ACT == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
-                t[i] = fmaf(alpha, x, rr4[i]);
+                for (int i = 0; i < 4; ++i) {
+                  float x = t[i];
+                  if (ACT == espb::ACT_RELU) x = fmaxf(x, 0.f);
+                  else if (ACT == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
+                  t[i] = fmaf(alpha, x, rr4[i]);
+                }
+                if (SPLIT) {
+                  float4 h, l;
+                  h.x = espb::tf32_hi(t[0]); h.y = espb::tf32_hi(t[1]); h.z = espb::tf32_hi(t[2]); h.w = espb::tf32_hi(t[3]);
+                  l.x = espb::tf32_lo(t[0], h.x); l.y = espb::tf32_lo(t[1], h.y); l.z = espb::tf32_lo(t[2], h.z); l.w = espb::tf32_lo(t[3], h.w);
+                  *reinterpret_cast<float4*>(cpi) = h;
+                  *reinterpret_cast<float4*>(cpi + cpl) = l;
+                } else {
+                  *reinterpret_cast<float4*>(cpi) = make_float4(t[0], t[1], t[2], t[3]);
+                }
+              } else if (c_part) {   // the one float4 per row that straddles N
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+                for (int i = 0; i < 4 && col + i < Ncols; ++i) {
+                  const float tt = epi_value(ea, vv[i], row0 + rsub + rl, col + i);
+                  if (SPLIT) { const float hh2 = espb::tf32_hi(tt); cpi[i] = hh2; cpi[cpl + i] = espb::tf32_lo(tt, hh2); }
+                  else cpi[i] = tt;
+                }
               }
-              if (SPLIT) {
-                float4 h, l;
-                h.x = espb::tf32_hi(t[0]); h.y = espb::tf32_hi(t[1]); h.z = espb::tf32_hi(t[2]); h.w = espb::tf32_hi(t[3]);
-                l.x = espb::tf32_lo(t[0], h.x); l.y = espb::tf32_lo(t[1], h.y); l.z = espb::tf32_lo(t[2], h.z); l.w = espb::tf32_lo(t[3], h.w);
-                *reinterpret_cast<float4*>(cp) = h;
-                *reinterpret_cast<float4*>(cp + cpl) = l;
-              } else {
-                *reinterpret_cast<float4*>(cp) = make_float4(t[0], t[1], t[2], t[3]);
-              }
-            } else {
-              const float vv[4] = {v.x, v.y, v.z, v.w};
-              const long long row = row0 + rsub + rl;
-#pragma unroll
+            }
+          }
+        }
+      } else {
+        // unaligned output / residual / bias (never on the hot path): scalar stores
+#pragma unroll 1
+        for (int j = 0; j < CW / 32; ++j) {
+          const int colb = n0 + half * CW + j * 32;
+          if (row0 >= p.M || colb >= Ncols) continue;
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {
+            __syncwarp();
+            if ((lane >> 4) == hh) {
+              for (int i = 0; i < 32; ++i) wrow[i] = acc_at(acc, j * 32 + i);
+            }
+            __syncwarp();
+            for (int it = 0; it < 4; ++it) {
+              const int rl = hh * 16 + it * 4;
+              if (rl >= rows_left) continue;
               for (int i = 0; i < 4; ++i) {
-                if (col + i < Ncols) {
-                  const float tt = epi_value(ea, vv[i], row, col + i);
-                  if (split) { const float hh2 = espb::tf32_hi(tt); cp[i] = hh2; cp[cpl + i] = espb::tf32_lo(tt, hh2); }
-                  else cp[i] = tt;
+                const int col = colb + c4 + i;
+                if (col < Ncols) {
+                  const long long row = row0 + rsub + rl;
+                  const float tt = epi_value(ea, rbase[it * 4 * 36 + i], row, col);
+                  float* cpe = ea.C + row * ldc + col;
+                  if (SPLIT) { const float hh2 = espb::tf32_hi(tt); cpe[0] = hh2; cpe[cpl] = espb::tf32_lo(tt, hh2); }
+                  else cpe[0] = tt;
                 }
               }
             }
