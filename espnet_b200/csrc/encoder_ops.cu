@@ -136,6 +136,8 @@ __global__ void v_transpose_kernel(const float* __restrict__ qkv, long long qkv_
 
 // scores = (ac[i][j] + bd[i][T-1-i+j]) / sqrt(dk) (rel_shift, attention.py:391-414,455-457); keys j >= len masked
 // (masked_fill(min) -> softmax -> masked_fill(0), attention.py:136-141). One warp per (b,h,i) row. Output split probs [.][Tp].
+// NV > 0: the row (len <= 32*NV keys) is held in registers, so ac / bd are read exactly once; NV == 0: three-pass fallback.
+template <int NV>
 __global__ void __launch_bounds__(256) relpos_softmax_kernel(const float* __restrict__ ac, const float* __restrict__ bd, int B, int H, int T, int Tp,
                                                              int Rp, const int* __restrict__ lens, float inv_scale_div,
                                                              float* __restrict__ probs, long long probs_plane) {
@@ -148,6 +150,31 @@ __global__ void __launch_bounds__(256) relpos_softmax_kernel(const float* __rest
   const float* ar = ac + rowid * Tp;
   const float* br = bd + rowid * Rp + (T - 1 - i);
   float* pr = probs + rowid * Tp;
+  if (NV > 0) {
+    float v[NV > 0 ? NV : 1];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int j = lane + 32 * k;
+      v[k] = (j < len) ? (__ldg(ar + j) + __ldg(br + j)) / inv_scale_div : -INFINITY;
+      mx = fmaxf(mx, v[k]);
+    }
+    mx = espb::warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      v[k] = (lane + 32 * k < len) ? expf(v[k] - mx) : 0.f;
+      sum += v[k];
+    }
+    sum = espb::warp_sum(sum);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int j = lane + 32 * k;
+      if (j < Tp) store_split(pr + j, probs_plane, v[k] / sum);
+    }
+    for (int j = lane + 32 * NV; j < Tp; j += 32) store_split(pr + j, probs_plane, 0.f);
+    return;
+  }
   float mx = -INFINITY;
   for (int j = lane; j < len; j += 32) mx = fmaxf(mx, (ar[j] + br[j]) / inv_scale_div);
   mx = espb::warp_max(mx);
@@ -266,7 +293,11 @@ int espb_v_transpose_f32(const float* qkv, long long qkv_plane, int B, int Tmax,
 int espb_relpos_softmax_f32(const float* ac, const float* bd, int B, int H, int T, int Tp, int Rp, const int* lens, float sqrt_dk, float* probs,
                             long long probs_plane, cudaStream_t stream) {
   long long rows = (long long)B * H * T;
-  relpos_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (T <= 256) relpos_softmax_kernel<8><<<grid, 256, 0, stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
+  else if (T <= 512) relpos_softmax_kernel<16><<<grid, 256, 0, stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
+  else if (T <= 1024) relpos_softmax_kernel<32><<<grid, 256, 0, stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
+  else relpos_softmax_kernel<0><<<grid, 256, 0, stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
