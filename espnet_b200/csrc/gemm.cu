@@ -249,6 +249,167 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------ 1-CTA tiles with the A operand multicast across a cluster
+// Small-M (decode-step) problems are bound by the per-SM TMA ingest rate (~32 B/cycle): the MC CTAs of a cluster compute MC
+// neighbouring n-tiles of the same m-tile, each fetches 1/MC of the A tile and multicasts it to all of them, so every CTA ingests
+// A/MC + B instead of A + B.  A stage is refilled only after all MC consumers released it (their tcgen05.commit arrives on the
+// empty barrier of every CTA of the cluster).
+__device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank_v();
+__device__ __forceinline__ void cluster_sync_all_v();
+
+template <int BN, int STAGES, int MC>
+__global__ void __cluster_dims__(1, MC, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32x3_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym, int axm, int aym) {
+  constexpr int B_TILE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
+  const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * STAGES, tmem_full_bar = bar_base + 16 * STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 16 * STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int bx = blockIdx.z % p.nbx, by = blockIdx.z / p.nbx;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const uint32_t rank = cluster_ctarank_v();            // position of this n-tile inside its cluster
+  constexpr uint16_t MASK = (uint16_t)((1u << MC) - 1);
+  constexpr int SLICE_ROWS = BM / MC, SLICE_BYTES = SLICE_ROWS * 128;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, MC); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all_v();     // every CTA's barriers are initialised before any multicast / remote arrive can reach them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        const uint32_t fb = full_bar + 8 * s;
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        {
+          const int ko = (p.kob > 0) ? kb / p.kob : 0;
+          const int ki = (p.kob > 0) ? kb % p.kob : kb;
+          const int mrow = m0 + (int)rank * SLICE_ROWS;          // this CTA's slice of the shared A tile, delivered to all MC CTAs
+          tma_load_5d_mc(sa + rank * SLICE_BYTES, &tmA, fb, ki * BK, mrow, bx * axm + ko, by * aym, 0, MASK);
+          tma_load_5d_mc(sa + A_TILE_BYTES + rank * SLICE_BYTES, &tmA, fb, ki * BK, mrow, bx * axm + ko, by * aym, 1, MASK);
+        }
+        tma_load_5d(sa + 2 * A_TILE_BYTES, &tmB, fb, kb * BK, n0, bx * bxm, by * bym, 0);
+        tma_load_5d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB, fb, kb * BK, n0, bx * bxm, by * bym, 1);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2 at bits 7,10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar + 8 * s, ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes
+          const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
+          const uint64_t b_hi = umma_desc(sa + 2 * A_TILE_BYTES + k * 32);
+          const uint64_t b_lo = umma_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + k * 32);
+          mma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | k) != 0);  // small terms first
+          mma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+          mma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+        }
+        tcgen05_commit_mc(empty_bar + 8 * s, MASK);  // releases this stage in every CTA of the cluster once these MMAs retire
+      }
+      tcgen05_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    EpiArgs e;
+    const long long coff = (long long)by * p.sc_y + (long long)bx * p.sc_x;
+    e.C = p.C + coff; e.c_plane = p.c_plane; e.ldc = p.ldc; e.split_out = p.split_out;
+    e.bias = p.bias ? p.bias + (long long)bx * p.sbias_x : nullptr; e.R = p.R ? p.R + (long long)by * p.sr_y + (long long)bx * p.sr_x : nullptr;
+    e.ldr = p.ldr; e.alpha = p.alpha; e.act = p.act;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((coff & 3) == 0) && ((p.c_plane & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      const int col0 = n0 + c * 32;
+      float* crow = e.C + (long long)row * e.ldc;
+      if (!row_ok || col0 >= p.N) {
+        // nothing to store for this lane / column chunk (tile overhang)
+      } else if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o, l;
+          float t0 = epi_value(e, v[j], row, col0 + j), t1 = epi_value(e, v[j + 1], row, col0 + j + 1);
+          float t2 = epi_value(e, v[j + 2], row, col0 + j + 2), t3 = epi_value(e, v[j + 3], row, col0 + j + 3);
+          if (e.split_out) {
+            o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
+            l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
+            *reinterpret_cast<float4*>(crow + col0 + j) = o;
+            *reinterpret_cast<float4*>(crow + e.c_plane + col0 + j) = l;
+          } else {
+            o.x = t0; o.y = t1; o.z = t2; o.w = t3;
+            *reinterpret_cast<float4*>(crow + col0 + j) = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col < p.N) {
+            float t = epi_value(e, v[j], row, col);
+            if (e.split_out) {
+              float h = espb::tf32_hi(t);
+              crow[col] = h; crow[e.c_plane + col] = espb::tf32_lo(t, h);
+            } else {
+              crow[col] = t;
+            }
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all_v();     // peers may still multicast into / arrive on this CTA's smem until all are done
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ tensor-core kernel v2: CTA pair + chunked promotion
 // cta_group::2: a cluster of two CTAs computes a 256 x BN tile (UMMA M=256); each CTA stages its own 128 rows of A and
 // its half (BN/2 rows) of B, so per-SM L2->smem traffic per MMA is halved against the 1-CTA kernel. The fp32 accumulator of
@@ -269,6 +430,8 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank_v() { return cluster_ctarank(); }
+__device__ __forceinline__ void cluster_sync_all_v() { cluster_sync_all(); }
 __device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
       "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -759,6 +922,23 @@ int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDes
   }
 }
 
+template <int BN, int STAGES, int MC>
+int launch_tc_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
+  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * BN * 128) + 1024 + 16 * STAGES + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tf32x3_mc_kernel<BN, STAGES, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      espb_set_error("cudaFuncSetAttribute(max dynamic smem) failed");
+      return ESPB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.nbx * d.nby);
+  gemm_tf32x3_mc_kernel<BN, STAGES, MC><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
 }  // namespace
 
 int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version) {
@@ -808,6 +988,16 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
   }
   if (bn == 256) return launch_tc<256, 2>(tmA, tmB, d, bxm, bym, axm, aym, stream);
   if (bn == 128) return launch_tc<128, 3>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+  if (version == 2 && d.a_mode == 0 && d.band_t == 0 && ((d.N + 63) / 64) % 4 == 0) {
+    // decode-step problems: 4 neighbouring n-tiles share (multicast) the A tile; A box = 32 rows per CTA
+    long long n_outer = 1, k_inner = d.K;
+    if (d.kob > 0) { k_inner = (long long)d.kob * BK; n_outer = (d.K + k_inner - 1) / k_inner; }
+    long long dims[5] = {k_inner, d.M, (axm ? d.nbx : 1) + n_outer - 1, aym ? d.nby : 1, 2};
+    long long str[4] = {d.lda, d.sa_x, d.sa_y, d.a_plane};
+    rc = make_map(&tmA, d.A, dims, str, BM / 4);
+    if (rc != ESPB_OK) return rc;
+    return launch_tc_mc<64, 4, 4>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+  }
   return launch_tc<64, 4>(tmA, tmB, d, bxm, bym, axm, aym, stream);
 }
 
