@@ -200,6 +200,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     e.ldr = p.ldr; e.alpha = p.alpha; e.act = p.act;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((coff & 3) == 0) && ((p.c_plane & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool r_vec_ok = p.R && ((p.ldr & 3) == 0) && ((((long long)by * p.sr_y + (long long)bx * p.sr_x) & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
@@ -210,11 +212,28 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (!row_ok || col0 >= p.N) {
         // nothing to store for this lane / column chunk (tile overhang)
       } else if (vec_ok && col0 + 32 <= p.N) {
+        // residual (may alias the output: x += ...) and bias are fetched up front with 128-bit loads, so the 8 loads are in flight
+        // together instead of one dependent load -> store round trip per element
+        float rres[32];
+        if (e.R && r_vec_ok) {
+          const float4* rp4 = reinterpret_cast<const float4*>(e.R + (long long)row * e.ldr + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 t = rp4[j]; rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rres[j] = e.R ? e.R[(long long)row * e.ldr + col0 + j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j];
+          if (e.bias) x += __ldg(e.bias + col0 + j);
+          x = espb::apply_act_acc(x, e.act);
+          v[j] = fmaf(e.alpha, x, rres[j]);
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 o, l;
-          float t0 = epi_value(e, v[j], row, col0 + j), t1 = epi_value(e, v[j + 1], row, col0 + j + 1);
-          float t2 = epi_value(e, v[j + 2], row, col0 + j + 2), t3 = epi_value(e, v[j + 3], row, col0 + j + 3);
+          const float t0 = v[j], t1 = v[j + 1], t2 = v[j + 2], t3 = v[j + 3];
           if (e.split_out) {
             o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
             l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
@@ -360,6 +379,8 @@ gemm_tf32x3_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     e.ldr = p.ldr; e.alpha = p.alpha; e.act = p.act;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((coff & 3) == 0) && ((p.c_plane & 3) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool r_vec_ok = p.R && ((p.ldr & 3) == 0) && ((((long long)by * p.sr_y + (long long)bx * p.sr_x) & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       float v[32];
@@ -370,11 +391,28 @@ gemm_tf32x3_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (!row_ok || col0 >= p.N) {
         // nothing to store for this lane / column chunk (tile overhang)
       } else if (vec_ok && col0 + 32 <= p.N) {
+        // residual (may alias the output: x += ...) and bias are fetched up front with 128-bit loads, so the 8 loads are in flight
+        // together instead of one dependent load -> store round trip per element
+        float rres[32];
+        if (e.R && r_vec_ok) {
+          const float4* rp4 = reinterpret_cast<const float4*>(e.R + (long long)row * e.ldr + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 t = rp4[j]; rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rres[j] = e.R ? e.R[(long long)row * e.ldr + col0 + j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j];
+          if (e.bias) x += __ldg(e.bias + col0 + j);
+          x = espb::apply_act_acc(x, e.act);
+          v[j] = fmaf(e.alpha, x, rres[j]);
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 o, l;
-          float t0 = epi_value(e, v[j], row, col0 + j), t1 = epi_value(e, v[j + 1], row, col0 + j + 1);
-          float t2 = epi_value(e, v[j + 2], row, col0 + j + 2), t3 = epi_value(e, v[j + 3], row, col0 + j + 3);
+          const float t0 = v[j], t1 = v[j + 1], t2 = v[j + 2], t3 = v[j + 3];
           if (e.split_out) {
             o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
             l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
@@ -979,6 +1017,7 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
   else if (d.N <= 128) bn = 128;
   else if (tiles_m * ((d.N + 255) / 256) * nb >= 148) bn = 256;
   else if (tiles_m * ((d.N + 127) / 128) * nb >= 148) bn = 128;
+  else if (tiles_m * ((d.N + 63) / 64) * nb > 148) bn = 128;   // one CTA per SM (192 KB smem): more than 148 tiles would run as two waves
   else bn = 64;
   {
     long long dims[5] = {d.K, d.N, bxm ? d.nbx : 1, bym ? d.nby : 1, 2};
@@ -987,8 +1026,8 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
     if (rc != ESPB_OK) return rc;
   }
   if (bn == 256) return launch_tc<256, 2>(tmA, tmB, d, bxm, bym, axm, aym, stream);
-  if (bn == 128) return launch_tc<128, 3>(tmA, tmB, d, bxm, bym, axm, aym, stream);
-  if (version == 2 && d.a_mode == 0 && d.band_t == 0 && ((d.N + 63) / 64) % 4 == 0) {
+  const bool mc_ok = version == 2 && d.a_mode == 0 && d.band_t == 0 && ((d.N + bn - 1) / bn) % 4 == 0 && bn <= 128;
+  if (mc_ok) {
     // decode-step problems: 4 neighbouring n-tiles share (multicast) the A tile; A box = 32 rows per CTA
     long long n_outer = 1, k_inner = d.K;
     if (d.kob > 0) { k_inner = (long long)d.kob * BK; n_outer = (d.K + k_inner - 1) / k_inner; }
@@ -996,8 +1035,10 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
     long long str[4] = {d.lda, d.sa_x, d.sa_y, d.a_plane};
     rc = make_map(&tmA, d.A, dims, str, BM / 4);
     if (rc != ESPB_OK) return rc;
+    if (bn == 128) return launch_tc_mc<128, 3, 4>(tmA, tmB, d, bxm, bym, axm, aym, stream);
     return launch_tc_mc<64, 4, 4>(tmA, tmB, d, bxm, bym, axm, aym, stream);
   }
+  if (bn == 128) return launch_tc<128, 3>(tmA, tmB, d, bxm, bym, axm, aym, stream);
   return launch_tc<64, 4>(tmA, tmB, d, bxm, bym, axm, aym, stream);
 }
 
