@@ -5,7 +5,7 @@ import torch
 import os
 
 pytestmark = pytest.mark.gpu
-MODES = [m for m in os.environ.get("ESPB_TEST_GEMM_MODES", "simt,tc").split(",") if m]
+MODES = [m for m in os.environ.get("ESPB_TEST_GEMM_MODES", "simt,tc,tc2").split(",") if m]
 
 
 def _split(x):

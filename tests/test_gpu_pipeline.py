@@ -19,7 +19,7 @@ from gpu_util import build_cuda_model, random_weights, refbuild, speech2text
 
 pytestmark = pytest.mark.gpu
 
-GEMM_MODES = [m for m in os.environ.get("ESPB_TEST_GEMM_MODES", "simt,tc").split(",") if m]
+GEMM_MODES = [m for m in os.environ.get("ESPB_TEST_GEMM_MODES", "simt,tc,tc2").split(",") if m]
 
 
 @pytest.fixture(params=GEMM_MODES)
@@ -183,3 +183,56 @@ def test_too_short_utterance_raises():
     s2t = speech2text(cfg, w, beam_size=2, ctc_weight=0.3)
     with pytest.raises(espnet_b200.TooShortUttError):
         s2t(torch.zeros(700))
+
+
+def test_config0_ctc_greedy_8x5s_vs_oracle():
+    """BASELINE.json configs[0]: Conformer 4L/256d/4h (ff 2048, kernel 31), V=5000, CTC-greedy, 8 x 5 s -- token ids bit-exact against the
+    CPU oracle (identity is demanded for every utterance whose smallest top-2 logit gap exceeds 20x the measured logit error)."""
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    cfg = dict(d_model=256, heads=4, ff=2048, enc_layers=4, dec_layers=1, vocab=5000, kernel=31)
+    w = random_weights(cfg, seed=0)
+    s2t = speech2text(cfg, w, beam_size=2, ctc_weight=0.3)
+    o = oracle.OracleSpeech2Text(cfg, w, beam_size=2, ctc_weight=0.3)
+    waves = [refbuild.waveform(i, 80000) for i in range(8)]
+    got = s2t.ctc_greedy(waves)
+    speech, sl = s2t._to_batch(waves)
+    enc, elens = s2t.asr_model.encode(speech, sl)
+    lg = s2t.asr_model.ctc.logits(enc)
+    checked = 0
+    for i, wv in enumerate(waves):
+        ref_enc = o.encode(wv)
+        ref_lg = OE.ctc_logits(ref_enc, o.w)
+        err = _maxerr(lg[i, : ref_lg.shape[0]], ref_lg)
+        top2 = ref_lg.topk(2, dim=-1)[0]
+        margin = (top2[:, 0] - top2[:, 1]).min().item()
+        _, ids = OE.ctc_greedy(ref_enc, o.w)
+        print(f"utt{i}: logit max abs err {err:.2e}, min top-2 margin {margin:.2e}, tokens {len(ids)}")
+        assert err < 2e-3
+        if margin > 20 * err:
+            assert got[i] == ids.tolist()
+            checked += 1
+        else:  # frames inside the error band may flip: demand identity of all frames whose own margin is safe
+            am_ref = ref_lg.argmax(-1)
+            am_got = lg[i, : ref_lg.shape[0]].argmax(-1).cpu()
+            safe = (top2[:, 0] - top2[:, 1]) > 20 * err
+            assert bool((am_ref[safe] == am_got[safe]).all())
+    print(f"{checked}/8 utterances compared for exact token identity")
+
+
+def test_config1_like_joint_decode_vs_oracle():
+    """Conformer (4L/256d) + 2L decoder, V=5000, joint CTC/attention beam 10 on 2 x 5 s, first 6 steps: identical n-best sequences."""
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    cfg = dict(d_model=256, heads=4, ff=1024, enc_layers=2, dec_layers=2, vocab=5000, kernel=31)
+    w = random_weights(cfg, seed=3)
+    kw = dict(beam_size=10, ctc_weight=0.3, maxlenratio=-6.0, nbest=3)
+    s2t = speech2text(cfg, w, **kw)
+    o = oracle.OracleSpeech2Text(cfg, w, **kw)
+    waves = [refbuild.waveform(100 + i, 80000) for i in range(2)]
+    res = s2t.batch_decode(waves)
+    for i, wv in enumerate(waves):
+        ref = o(wv)
+        assert len(res[i]) == len(ref)
+        for a, b in zip(res[i], ref):
+            print(a[3].yseq.tolist(), a[3].score, b[3].score)
+            assert a[3].yseq.tolist() == b[3].yseq.tolist()
+            assert abs(a[3].score - b[3].score) <= 2e-4 * max(1.0, abs(b[3].score))
