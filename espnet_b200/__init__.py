@@ -11,7 +11,7 @@ from .ctc import CTC  # noqa: F401
 from .decoder import TransformerDecoder  # noqa: F401
 from .encoder import ConformerEncoder  # noqa: F401
 from .errors import TooShortUttError  # noqa: F401
-from .frontend import DefaultFrontend, LogMel, UtteranceMVN  # noqa: F401
+from .frontend import DefaultFrontend, GlobalMVN, LogMel, UtteranceMVN  # noqa: F401
 from .search import BatchBeamSearch, Hypothesis  # noqa: F401
 
 __version__ = "0.1.0"

@@ -22,14 +22,14 @@ from .ctc import CTC
 from .decoder import TransformerDecoder
 from .encoder import ConformerEncoder
 from .errors import TooShortUttError  # noqa: F401
-from .frontend import DefaultFrontend, UtteranceMVN
+from .frontend import DefaultFrontend, GlobalMVN, UtteranceMVN
 from .search import BatchBeamSearch, Hypothesis
 
 logger = logging.getLogger(__name__)
 
 # name -> class registries, as espnet2/tasks/asr.py:95-206 (only the classes on the north-star path)
 frontend_choices = {"default": DefaultFrontend}
-normalize_choices = {"utterance_mvn": UtteranceMVN}
+normalize_choices = {"global_mvn": GlobalMVN, "utterance_mvn": UtteranceMVN}
 encoder_choices = {"conformer": ConformerEncoder}
 decoder_choices = {"transformer": TransformerDecoder}
 

@@ -189,6 +189,22 @@ __global__ void utt_mvn_feat_kernel(float* __restrict__ feats, const long long* 
   }
 }
 
+// GlobalMVN.forward (espnet2/layers/global_mvn.py:74-103): (x - mean) on valid frames, padded frames 0, then / std.
+__global__ void global_mvn_kernel(float* __restrict__ feats, const long long* __restrict__ feat_lens, int Tmax, int D, const float* __restrict__ mean,
+                                  const float* __restrict__ stdv, int norm_means, int norm_vars) {
+  const int b = blockIdx.y;
+  const long long n = (long long)Tmax * D;
+  const int Tf = (int)feat_lens[b];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / D), d = (int)(i % D);
+    float v = feats[(long long)b * n + i];
+    if (norm_means) v -= mean[d];
+    if (t >= Tf) v = 0.f;
+    if (norm_vars) v /= stdv[d];
+    feats[(long long)b * n + i] = v;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -222,6 +238,14 @@ int espb_utt_mvn_f32(float* feats, const long long* feat_lens, int B, int Tf_max
   dim3 grid(nblk, B);
   feat_colsum_kernel<<<grid, 128, 0, stream>>>(feats, feat_lens, Tf_max, n_mels, partial_ws, nblk);
   utt_mvn_feat_kernel<<<grid, 256, 0, stream>>>(feats, feat_lens, Tf_max, n_mels, partial_ws, nblk);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_global_mvn_f32(float* feats, const long long* feat_lens, int B, int Tmax, int D, const float* mean, const float* stdv, int norm_means,
+                        int norm_vars, cudaStream_t stream) {
+  dim3 grid(64, B);
+  global_mvn_kernel<<<grid, 256, 0, stream>>>(feats, feat_lens, Tmax, D, mean, stdv, norm_means, norm_vars);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

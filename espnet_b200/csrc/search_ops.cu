@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
 template <int UN, int WC, int DKC>
 __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __restrict__ q, const float* __restrict__ kmem, const float* __restrict__ vmem,
                                                            int Tmax, const int* __restrict__ lens, int W_rt, int D, int H, int lpr_rt /* pow2 >= dk/4 */,
-                                                           float* __restrict__ ctx, long long ctx_plane) {
+                                                           float* __restrict__ ctx, long long ctx_plane, int w0, int Wall) {
   extern __shared__ float sm[];  // q [W][dk] | scores [W][Tmax] (reused for the cross-warp PV reduction) | K tile [128][dk+4]
   constexpr bool CT = (WC > 0);
   constexpr int JMAX = CT ? (WC + 1) / 2 : 8;          // beam slots per half block
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __res
   float* qs = sm;
   float* sc = qs + W * dk;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < W * dk; i += blockDim.x) qs[i] = q[((long long)(u * W + i / dk)) * D + h * dk + (i % dk)];
+  for (int i = threadIdx.x; i < W * dk; i += blockDim.x) qs[i] = q[((long long)(u * Wall + w0 + i / dk)) * D + h * dk + (i % dk)];   // slots w0 .. w0+W-1 of the Wall beam slots
   __syncthreads();
   const int rpw = 32 / lpr;                 // rows per warp instruction
   const int rsub = lane / lpr, c4 = lane % lpr;   // row within the group, float4 column
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __res
   for (int i = threadIdx.x; i < W * dk; i += blockDim.x) {
     float a = 0.f;
     for (int g = 0; g < hw; ++g) a += red[(long long)g * W * dk + i];
-    store_split(ctx + ((long long)(u * W + i / dk)) * D + h * dk + (i % dk), ctx_plane, a);
+    store_split(ctx + ((long long)(u * Wall + w0 + i / dk)) * D + h * dk + (i % dk), ctx_plane, a);
   }
 }
 
@@ -262,7 +262,7 @@ __device__ __forceinline__ void mma3_tf32(float (&c)[4], const uint32_t (&ah)[4]
 
 __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ kmem, const float* __restrict__ vmem,
                                                                   int Tmax, const int* __restrict__ lens, int W, int D, int H,
-                                                                  float* __restrict__ ctx, long long ctx_plane) {
+                                                                  float* __restrict__ ctx, long long ctx_plane, int w0, int Wall) {
   constexpr int DK = 64, QST = 68, KST = 68, VST = 72;
   extern __shared__ float sm[];  // q [16][68] | scores [W][Tmax] (pad 4; reused for the cross-warp reduction) | tile [128][72]
   const int u = blockIdx.x / H, h = blockIdx.x % H;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* _
   const int g = lane >> 2, t4 = lane & 3;
   for (int i = threadIdx.x; i < 16 * DK; i += blockDim.x) {
     const int w = i / DK, d = i % DK;
-    qs[w * QST + d] = (w < W) ? q[((long long)(u * W + w)) * D + h * DK + d] : 0.f;
+    qs[w * QST + d] = (w < W) ? q[((long long)(u * Wall + w0 + w)) * D + h * DK + d] : 0.f;
   }
   const float4* kb = reinterpret_cast<const float4*>(kmem + ((long long)(u * H + h) * Tmax) * DK);
   const float4* vb = reinterpret_cast<const float4*>(vmem + ((long long)(u * H + h) * Tmax) * DK);
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* _
     float a = 0.f;
 #pragma unroll
     for (int ww = 0; ww < 8; ++ww) a += red[((long long)ww * 16 + w) * DK + d];
-    store_split(ctx + ((long long)(u * W + w)) * D + h * DK + d, ctx_plane, a);
+    store_split(ctx + ((long long)(u * Wall + w0 + w)) * D + h * DK + d, ctx_plane, a);
   }
 }
 
@@ -549,6 +549,7 @@ struct BeamState {
 // mode 1: joint             -- candidates j<P from the pre-beam + eos as candidate P; part/valid [n][P+1]
 //                              total = ((dec + penalty) + w_ctc*part) + score   (batch_beam_search.py:293-309)
 // mode 2: CTC only (dense)  -- cand_val[n][P] = w_ctc*part of cand_ids, part = dense [n][V]
+template <int MAXC>   // each lane owns candidates lane, lane+32, ...: supports W*PC <= 32*MAXC
 __global__ void __launch_bounds__(32) beam_select_kernel(BeamState st, int U, int W, int P, int V, int step, const int* __restrict__ step_ptr,
                                                          const int* __restrict__ maxlen,
                                                          const int* __restrict__ minlen, int eos, float w_dec, float w_ctc, float penalty, int mode,
@@ -559,7 +560,6 @@ __global__ void __launch_bounds__(32) beam_select_kernel(BeamState st, int U, in
   const int u = blockIdx.x, lane = threadIdx.x;
   const int PC = (mode == 1) ? P + 1 : P;   // candidates per slot
   const int total = W * PC;
-  constexpr int MAXC = 24;                  // each lane owns candidates lane, lane+32, ...: supports W*PC <= 768
   float tot[MAXC];
   const bool done = st.utt_done[u] != 0;
 #pragma unroll
@@ -749,49 +749,50 @@ int espb_dec_self_attn_f32(const float* qkv, float* kc, float* vc, const int* an
 int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, int U, int Tmax, const int* lens, int W, int D, int H, float* ctx,
                           long long ctx_plane, cudaStream_t stream) {
   const int dk = D / H;
-  if (W > 16 || dk > 128 || (dk & 3)) { espb_set_error("dec_src_attn: needs beam <= 16 and d_k a multiple of 4, <= 128"); return ESPB_ERR_ARG; }
+  if (W > 64 || dk > 128 || (dk & 3)) { espb_set_error("dec_src_attn: needs beam <= 64 and d_k a multiple of 4, <= 128"); return ESPB_ERR_ARG; }
   int lpr = 1;
   while (lpr * 4 < dk) lpr <<= 1;
-  const size_t red = (size_t)8 * W * dk, scs = ((size_t)W * Tmax + 3) & ~(size_t)3;
-  const size_t smem = ((size_t)W * dk + (scs > red ? scs : red) + (size_t)128 * (dk + 4)) * sizeof(float);
-  if (smem > 200 * 1024) { espb_set_error("dec_src_attn: beam*T too large for shared memory"); return ESPB_ERR_ARG; }
-  if (dk == 64 && !getenv("ESPNET_B200_SRC_ATTN_FFMA")) {
-    const size_t scs4 = ((size_t)W * Tmax + 3) & ~(size_t)3;
-    const size_t need = (16 * 68 + scs4 + 128 * 72) * sizeof(float);
-    const size_t redb = (size_t)8 * 16 * 64 * sizeof(float);
-    const size_t smem_mma = need > 16 * 68 * sizeof(float) + redb ? need : 16 * 68 * sizeof(float) + redb;
-    if (smem_mma <= 200 * 1024) {
-      static bool attr = false;
-      if (!attr) {
-        if (cudaFuncSetAttribute(dec_src_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
-          espb_set_error("dec_src_attn: cannot raise dynamic shared memory"); return ESPB_ERR_CUDA;
+  for (int w0 = 0; w0 < W; w0 += 16) {   // the kernels keep <= 16 beam slots per block; wider beams stream K/V once per group of 16
+    const int Wg = (W - w0 < 16) ? W - w0 : 16;
+    if (dk == 64 && !getenv("ESPNET_B200_SRC_ATTN_FFMA")) {
+      const size_t scs4 = ((size_t)Wg * Tmax + 3) & ~(size_t)3;
+      const size_t need = (16 * 68 + scs4 + 128 * 72) * sizeof(float);
+      if (need <= 200 * 1024) {
+        static bool attr = false;
+        if (!attr) {
+          if (cudaFuncSetAttribute(dec_src_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
+            espb_set_error("dec_src_attn: cannot raise dynamic shared memory"); return ESPB_ERR_CUDA;
+          }
+          attr = true;
         }
-        attr = true;
+        dec_src_attn_mma_kernel<<<U * H, 256, need, stream>>>(q, kmem, vmem, Tmax, lens, Wg, D, H, ctx, ctx_plane, w0, W);
+        ESPB_CHECK_LAUNCH();
+        continue;
       }
-      dec_src_attn_mma_kernel<<<U * H, 256, smem_mma, stream>>>(q, kmem, vmem, Tmax, lens, W, D, H, ctx, ctx_plane);
-      ESPB_CHECK_LAUNCH();
-      return ESPB_OK;
     }
-  }
-  using KernelFn = void (*)(const float*, const float*, const float*, int, const int*, int, int, int, int, float*, long long);
-  KernelFn fn = dec_src_attn_kernel<4, 0, 0>;
-  if (dk == 64) {
-    switch (W) {
-      case 4: fn = dec_src_attn_kernel<4, 4, 64>; break;
-      case 5: fn = dec_src_attn_kernel<4, 5, 64>; break;
-      case 8: fn = dec_src_attn_kernel<4, 8, 64>; break;
-      case 10: fn = dec_src_attn_kernel<4, 10, 64>; break;
-      case 16: fn = dec_src_attn_kernel<4, 16, 64>; break;
-      default: break;
+    const size_t red = (size_t)8 * Wg * dk, scs = ((size_t)Wg * Tmax + 3) & ~(size_t)3;
+    const size_t smem = ((size_t)Wg * dk + (scs > red ? scs : red) + (size_t)128 * (dk + 4)) * sizeof(float);
+    if (smem > 200 * 1024) { espb_set_error("dec_src_attn: beam*T too large for shared memory"); return ESPB_ERR_ARG; }
+    using KernelFn = void (*)(const float*, const float*, const float*, int, const int*, int, int, int, int, float*, long long, int, int);
+    KernelFn fn = dec_src_attn_kernel<4, 0, 0>;
+    if (dk == 64) {
+      switch (Wg) {
+        case 4: fn = dec_src_attn_kernel<4, 4, 64>; break;
+        case 5: fn = dec_src_attn_kernel<4, 5, 64>; break;
+        case 8: fn = dec_src_attn_kernel<4, 8, 64>; break;
+        case 10: fn = dec_src_attn_kernel<4, 10, 64>; break;
+        case 16: fn = dec_src_attn_kernel<4, 16, 64>; break;
+        default: break;
+      }
     }
-  }
-  if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
-      espb_set_error("dec_src_attn: cannot raise dynamic shared memory"); return ESPB_ERR_CUDA;
+    if (smem > 48 * 1024) {
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
+        espb_set_error("dec_src_attn: cannot raise dynamic shared memory"); return ESPB_ERR_CUDA;
+      }
     }
+    fn<<<U * H, 256, smem, stream>>>(q, kmem, vmem, Tmax, lens, Wg, D, H, lpr, ctx, ctx_plane, w0, W);
+    ESPB_CHECK_LAUNCH();
   }
-  fn<<<U * H, 256, smem, stream>>>(q, kmem, vmem, Tmax, lens, W, D, H, lpr, ctx, ctx_plane);
-  ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
 
@@ -840,11 +841,18 @@ int espb_beam_select(const float* score, const float* sc_dec, const float* sc_ct
                      float w_dec, float w_ctc, float penalty, int mode, const int* cand_ids, const float* cand_val, const float* logp_dec,
                      const float* part, const int* valid, int end_detect, int maxlen_cap, cudaStream_t stream) {
   const int PC = (mode == 1) ? P + 1 : P;
-  if (W * PC > 768 || W > 32 || mode < 0 || mode > 2) { espb_set_error("beam_select: beam * candidates > 768 or bad mode"); return ESPB_ERR_ARG; }
+  if (W * PC > 1664 || W > 32 || mode < 0 || mode > 2) { espb_set_error("beam_select: beam * candidates > 1664 or bad mode"); return ESPB_ERR_ARG; }
   BeamState st{score, sc_dec, sc_ctc, active, n_score, n_sc_dec, n_sc_ctc, n_active, n_last_tok, n_parent, bp_parent, bp_token,
                ended_count, ended_step, ended_slot, ended_score, ended_dec, ended_ctc, ended_cap, best_at_step, best_all, utt_done};
-  beam_select_kernel<<<U, 32, 0, stream>>>(st, U, W, P, V, step, step_ptr, maxlen, minlen, eos, w_dec, w_ctc, penalty, mode, cand_ids, cand_val, logp_dec,
-                                           part, valid, end_detect, maxlen_cap);
+#define ESPB_BEAM_SELECT(MC)                                                                                                                     \
+  beam_select_kernel<MC><<<U, 32, 0, stream>>>(st, U, W, P, V, step, step_ptr, maxlen, minlen, eos, w_dec, w_ctc, penalty, mode, cand_ids, cand_val, \
+                                               logp_dec, part, valid, end_detect, maxlen_cap)
+  const int total = W * PC;
+  if (total <= 32 * 6) ESPB_BEAM_SELECT(6);
+  else if (total <= 32 * 12) ESPB_BEAM_SELECT(12);
+  else if (total <= 32 * 24) ESPB_BEAM_SELECT(24);
+  else ESPB_BEAM_SELECT(52);
+#undef ESPB_BEAM_SELECT
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

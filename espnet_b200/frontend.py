@@ -147,3 +147,38 @@ class UtteranceMVN(torch.nn.Module):
             call("espb_utt_mvn_f32", ptr(x), ptr(lens_dev), B, T, D, ptr(ws))
             _count(2)
         return x, ilens
+
+
+class GlobalMVN(torch.nn.Module):
+    """espnet2/layers/global_mvn.py:12-103: mean/variance normalisation with statistics from an npy/npz file (same buffers
+    ``mean`` / ``std``).  In place like the reference."""
+
+    def __init__(self, stats_file, norm_means: bool = True, norm_vars: bool = True, eps: float = 1.0e-20):
+        super().__init__()
+        self.norm_means, self.norm_vars, self.eps, self.stats_file = norm_means, norm_vars, eps, stats_file
+        stats = np.load(stats_file)
+        if isinstance(stats, np.ndarray):   # Kaldi-like stats
+            count = stats[0].flatten()[-1]
+            mean = stats[0, :-1] / count
+            var = stats[1, :-1] / count - mean * mean
+        else:
+            count, sum_v, sum_square_v = stats["count"], stats["sum"], stats["sum_square"]
+            mean = sum_v / count
+            var = sum_square_v / count - mean * mean
+        std = np.sqrt(np.maximum(var, eps))
+        self.register_buffer("mean", torch.from_numpy(np.asarray(mean)))
+        self.register_buffer("std", torch.from_numpy(np.asarray(std)))
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, ilens: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        B, T, D = x.shape
+        if ilens is None:
+            ilens = torch.full((B,), T, dtype=torch.int64, device=x.device)
+        _PARTIAL_SUMS.pop(x.data_ptr(), None)
+        assert x.is_contiguous()
+        lens_dev = ilens.to(device=x.device, dtype=torch.int64).contiguous()
+        mean = self.mean.to(device=x.device, dtype=torch.float32).contiguous()
+        std = self.std.to(device=x.device, dtype=torch.float32).contiguous()
+        call("espb_global_mvn_f32", ptr(x), ptr(lens_dev), B, T, D, ptr(mean), ptr(std), int(self.norm_means), int(self.norm_vars))
+        _count()
+        return x, ilens

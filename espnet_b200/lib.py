@@ -39,6 +39,7 @@ _SIGS = {
     "espb_stft_logmel_f32": [P, P, I, I, P, P, P, P, P, P, I, P, I, P, P],
     "espb_utt_mvn_from_partial_f32": [P, P, I, I, I, P, P],
     "espb_utt_mvn_f32": [P, P, I, I, I, P, P],
+    "espb_global_mvn_f32": [P, P, I, I, I, P, P, I, I, P],
     "espb_layernorm_f32": [P, L, I, P, P, F, P, P, L, P],
     "espb_split_tf32_f32": [P, L, P, L, P],
     "espb_conv1_relu_f32": [P, I, I, I, P, P, I, P, I, I, I, I, P],

@@ -58,8 +58,8 @@ class BatchBeamSearch(torch.nn.Module):
         self.normalize_length = normalize_length
         self.full_scorers = {k: v for k, v in (("decoder", self.decoder),) if v is not None}
         self.part_scorers = {k: v for k, v in (("ctc", self.ctc),) if v is not None}
-        if beam_size > 16 and self.decoder is not None:
-            raise NotImplementedError("beam_size > 16 with an attention decoder")
+        if beam_size > 32:
+            raise NotImplementedError("beam_size > 32 (the per-utterance beam selection runs in one warp)")
 
     # ---------------------------------------------------------------- search state (cached per shape so that CUDA graphs can be reused)
     def _state(self, dev, U, Tmax, W, V, cap, mode, P):

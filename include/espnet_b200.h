@@ -67,6 +67,9 @@ int espb_stft_logmel_f32(const float* wave, const long long* wave_lens, int B, i
 int espb_utt_mvn_from_partial_f32(float* feats, const long long* wave_lens, int B, int Tf_max, int n_mels, const float* partial,
                                   cudaStream_t stream);
 int espb_utt_mvn_f32(float* feats, const long long* feat_lens, int B, int Tf_max, int n_mels, float* partial_ws, cudaStream_t stream);
+/* GlobalMVN.forward (espnet2/layers/global_mvn.py:74-103), in place: (x - mean) masked to the valid frames, then / std. */
+int espb_global_mvn_f32(float* feats, const long long* feat_lens, int B, int Tmax, int D, const float* mean, const float* stdv, int norm_means,
+                        int norm_vars, cudaStream_t stream);
 
 /* ---- Encoder glue kernels -----------------------------------------------------------------------------------
  * LayerNorm (transformer/layer_norm.py:12-42, eps 1e-12): out_plain and/or out_split may be NULL. */

@@ -60,6 +60,34 @@ def utterance_mvn(feats):
     return feats - feats.sum(dim=0, keepdim=True) / feats.shape[0]
 
 
+def global_mvn_stats(stats, eps=1.0e-20):
+    """mean / std from accumulated statistics (espnet2/layers/global_mvn.py:41-57): either a dict with
+    count / sum / sum_square, or a Kaldi-like [2][D+1] array whose last column holds the count."""
+    if isinstance(stats, np.ndarray):
+        count = stats[0].flatten()[-1]
+        mean = stats[0, :-1] / count
+        var = stats[1, :-1] / count - mean * mean
+    else:
+        count = stats["count"]
+        mean = stats["sum"] / count
+        var = stats["sum_square"] / count - mean * mean
+    return torch.from_numpy(np.asarray(mean)), torch.from_numpy(np.asarray(np.sqrt(np.maximum(var, eps))))
+
+
+def global_mvn(x, ilens, mean, std, norm_means=True, norm_vars=True):
+    """GlobalMVN.forward (espnet2/layers/global_mvn.py:74-103) on a padded batch [B][T][D]: subtract the
+    mean, zero the padded frames, divide by std (the float64 statistics are cast to x.dtype first, :86-87)."""
+    x = x.clone()
+    mean, std = mean.to(x.dtype), std.to(x.dtype)
+    pad = torch.arange(x.shape[1])[None, :] >= ilens[:, None]
+    if norm_means:
+        x -= mean.to(x.device)
+    x = x.masked_fill(pad[:, :, None], 0.0)
+    if norm_vars:
+        x /= std.to(x.device)
+    return x
+
+
 def frontend_forward(wave, melmat=None):
     """DefaultFrontend.forward for one single-channel utterance (frontend/default.py:82-117)."""
     melmat = slaney_mel_matrix() if melmat is None else melmat

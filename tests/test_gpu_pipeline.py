@@ -236,3 +236,82 @@ def test_config1_like_joint_decode_vs_oracle():
             print(a[3].yseq.tolist(), a[3].score, b[3].score)
             assert a[3].yseq.tolist() == b[3].yseq.tolist()
             assert abs(a[3].score - b[3].score) <= 2e-4 * max(1.0, abs(b[3].score))
+
+
+@pytest.mark.parametrize("heads,beam,ctc_weight", [(2, 20, 0.3), (8, 20, 0.3), (2, 32, 0.5), (8, 24, 0.0), (2, 20, 1.0)])
+def test_wide_beam_vs_oracle(heads, beam, ctc_weight):
+    """Beams wider than one cross-attention slot group (the reference default is beam 20): d_k = 64 takes the tensor-core
+    cross-attention, d_k = 16 the FFMA one; n-best identical to the oracle."""
+    cfg = dict(d_model=128, heads=heads, ff=256, enc_layers=2, dec_layers=2, vocab=80, kernel=15)
+    w = random_weights(cfg, seed=11)
+    kw = dict(beam_size=beam, ctc_weight=ctc_weight, maxlenratio=-8.0, nbest=5)
+    s2t = speech2text(cfg, w, **kw)
+    o = oracle.OracleSpeech2Text(cfg, w, **kw)
+    waves = [refbuild.waveform(40 + i, n) for i, n in enumerate([16000, 11000])]
+    res = s2t.batch_decode(waves)
+    for i, wv in enumerate(waves):
+        ref = o(wv)
+        assert len(res[i]) == len(ref)
+        for a, b in zip(res[i], ref):
+            assert a[3].yseq.tolist() == b[3].yseq.tolist()
+            assert abs(a[3].score - b[3].score) <= 2e-4 * max(1.0, abs(b[3].score))
+
+
+def test_beam_wider_than_32_is_refused():
+    z, cfg, w = load("tiny")
+    with pytest.raises(NotImplementedError):
+        speech2text(cfg, w, beam_size=33, ctc_weight=0.3)
+
+
+def test_global_mvn_bit_exact_vs_reference_fixture(tmp_path):
+    """GlobalMVN (espnet2/layers/global_mvn.py) for all four (norm_means, norm_vars) settings, npz and Kaldi-style stats files."""
+    import os
+
+    import espnet_b200
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gmvn.npz"))
+    stats = {k: z["stats_" + k] for k in ("count", "sum", "sum_square")}
+    f_npz, f_npy = str(tmp_path / "stats.npz"), str(tmp_path / "stats.npy")
+    np.savez(f_npz, **stats)
+    kaldi = np.zeros((2, 81))
+    kaldi[0, :80], kaldi[1, :80], kaldi[0, 80] = stats["sum"], stats["sum_square"], stats["count"]
+    np.save(f_npy, kaldi)
+    for f in (f_npz, f_npy):
+        for nm in (1, 0):
+            for nv in (1, 0):
+                m = espnet_b200.GlobalMVN(f, norm_means=bool(nm), norm_vars=bool(nv)).cuda()
+                x = torch.from_numpy(z["x"]).cuda()
+                y, ol = m(x, torch.from_numpy(z["ilens"]).cuda())
+                assert y.data_ptr() == x.data_ptr()
+                np.testing.assert_array_equal(y.cpu().numpy(), z[f"y_m{nm}_v{nv}"])
+                assert ol.tolist() == z["ilens"].tolist()
+
+
+def test_speech2text_with_global_mvn_vs_oracle(tmp_path):
+    """normalize: global_mvn in the model config (espnet2/tasks/asr.py normalize_choices) -- greedy ids and encoder output vs the oracle."""
+    import argparse
+
+    import espnet_b200
+
+    cfg = dict(d_model=64, heads=4, ff=128, enc_layers=2, dec_layers=1, vocab=50, kernel=15)
+    rng = np.random.RandomState(3)
+    data = rng.randn(500, 80) * 2.0 - 3.0
+    stats = dict(count=np.array(500), sum=data.sum(0), sum_square=(data * data).sum(0))
+    f = str(tmp_path / "feats_stats.npz")
+    np.savez(f, **stats)
+    y = refbuild.model_yaml(cfg)
+    y["normalize"], y["normalize_conf"] = "global_mvn", dict(stats_file=f)
+    args = argparse.Namespace(**y)
+    torch.manual_seed(5)
+    model = espnet_b200.build_model(args)
+    w = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    assert "normalize.mean" in w and "normalize.std" in w
+    model = model.cuda().eval()
+    wave = refbuild.waveform(9, 14000)
+    speech = wave[None].cuda()
+    enc, elens = model.encode(speech, torch.tensor([wave.numel()]).cuda())
+    feats = OF.frontend_forward(wave, w["frontend.logmel.melmat"])
+    mean, std = OF.global_mvn_stats(stats)
+    fn = OF.global_mvn(feats[None], torch.tensor([feats.shape[0]]), mean, std)[0]
+    ref = OE.conformer_encode(fn, w, cfg["heads"], cfg["enc_layers"])
+    assert _maxerr(enc[0, : ref.shape[0]], ref) < 2e-3

@@ -69,3 +69,22 @@ def test_too_short_utterance_raises():
     o = oracle.OracleSpeech2Text(cfg, w, beam_size=2, ctc_weight=0.3)
     with pytest.raises(E.TooShortUttError):
         o(torch.zeros(700))  # 6 frames < 7 (subsampling.py:43-44)
+
+
+def test_global_mvn_vs_reference_fixture():
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gmvn.npz"))
+    stats = {k: z["stats_" + k] for k in ("count", "sum", "sum_square")}
+    mean, std = Fr.global_mvn_stats(stats)
+    np.testing.assert_array_equal(mean.float().numpy(), z["mean"])   # the reference casts its buffers to x.dtype on first use
+    np.testing.assert_array_equal(std.float().numpy(), z["std"])
+    kaldi = np.zeros((2, 81))
+    kaldi[0, :80], kaldi[1, :80], kaldi[0, 80] = stats["sum"], stats["sum_square"], stats["count"]
+    mk, sk = Fr.global_mvn_stats(kaldi)
+    np.testing.assert_array_equal(mk.float().numpy(), z["mean"])
+    np.testing.assert_array_equal(sk.float().numpy(), z["std"])
+    for nm in (1, 0):
+        for nv in (1, 0):
+            y = Fr.global_mvn(torch.from_numpy(z["x"]), torch.from_numpy(z["ilens"]), mean, std, bool(nm), bool(nv))
+            np.testing.assert_array_equal(y.numpy(), z[f"y_m{nm}_v{nv}"])
