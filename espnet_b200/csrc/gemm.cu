@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <limits.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -443,6 +444,206 @@ gemm_tf32x3_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all_v();     // peers may still multicast into / arrive on this CTA's smem until all are done
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ 1-CTA tiles with K split across a cluster (decode-step GEMMs)
+// A decode step multiplies a few hundred rows by a weight matrix: there are far fewer 128 x BN tiles than SMs and each CTA's time is
+// the serial walk over K (TMA ingest + barrier round trips per k-block).  The SK CTAs of a cluster (cluster dim z) each accumulate
+// 1/SK of the k-blocks of the SAME output tile in their own TMEM; the partial tiles are then reduce-scattered through distributed
+// shared memory: CTA r finalises the 32-column chunks c with c % SK == r, adding the other CTAs' partials in ascending rank order
+// (fixed order -> deterministic) before the usual bias / activation / residual / hi-lo split epilogue.
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
+  float4 v;
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %4, %5;\n\t"
+      "ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [ra];\n\t}"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "r"(local_addr), "r"(rank)
+      : "memory");
+  return v;
+}
+
+template <int BN, int STAGES, int SK>
+__global__ void __cluster_dims__(1, 1, SK) __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32x3_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p) {
+  constexpr int B_TILE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  constexpr int NCHUNK = BN / 32;
+  static_assert(STAGES * STAGE_BYTES >= BN * BM * 4, "partial-tile staging must fit in the pipeline buffers");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
+  const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * STAGES, tmem_full_bar = bar_base + 16 * STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 16 * STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const uint32_t rank = cluster_ctarank_v();            // == blockIdx.z: which K slice
+  const int num_kb_all = (p.K + BK - 1) / BK;
+  const int kb_per = (num_kb_all + SK - 1) / SK;
+  const int kb0 = (int)rank * kb_per;
+  const int nkb = min(num_kb_all, kb0 + kb_per) - kb0;   // >= 1 (checked on the host)
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int q = warp & 3;                                // TMEM lane quarter of an epilogue warp
+  // staging layout: [chunk][j/4][row 0..127][4 floats] -> 128-bit conflict-free writes (lane = row) and 128-bit remote reads
+  const uint32_t stg_lane = smem_base + (uint32_t)(q * 32 + lane) * 16u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        const uint32_t fb = full_bar + 8 * s;
+        mbar_expect_tx(fb, STAGE_BYTES);
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const int k0 = (kb0 + i) * BK;
+        tma_load_5d(sa, &tmA, fb, k0, m0, 0, 0, 0);
+        tma_load_5d(sa + A_TILE_BYTES, &tmA, fb, k0, m0, 0, 0, 1);
+        tma_load_5d(sa + 2 * A_TILE_BYTES, &tmB, fb, k0, n0, 0, 0, 0);
+        tma_load_5d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB, fb, k0, n0, 0, 0, 1);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(full_bar + 8 * s, ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes
+          const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + A_TILE_BYTES + k * 32);
+          const uint64_t b_hi = umma_desc(sa + 2 * A_TILE_BYTES + k * 32);
+          const uint64_t b_lo = umma_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + k * 32);
+          mma_tf32(tmem_base, a_lo, b_hi, idesc, (i | k) != 0);  // small terms first
+          mma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+          mma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+        }
+        tcgen05_commit(empty_bar + 8 * s);
+      }
+      tcgen05_commit(tmem_full_bar);   // all MMAs retired: accumulators complete, pipeline smem no longer read
+    }
+  } else {
+    // phase 1: park the chunks other CTAs finalise in this CTA's (now idle) pipeline buffers
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; ++c) {
+      if ((uint32_t)(c % SK) == rank) continue;          // warp-uniform
+      float v[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const uint32_t a = stg_lane + (uint32_t)((c * 8 + j4) * BM) * 16u;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j4]), "f"(v[4 * j4 + 1]), "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3])
+                     : "memory");
+      }
+    }
+  }
+  __syncwarp();
+  cluster_sync_all_v();     // release/acquire: every CTA's parked partials are visible cluster-wide
+
+  if (warp >= 2) {
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    EpiArgs e;
+    e.C = p.C; e.c_plane = p.c_plane; e.ldc = p.ldc; e.split_out = p.split_out;
+    e.bias = p.bias; e.R = p.R; e.ldr = p.ldr; e.alpha = p.alpha; e.act = p.act;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((p.c_plane & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool r_vec_ok = p.R && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; ++c) {
+      if ((uint32_t)(c % SK) != rank) continue;
+      float v[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+      for (int r = 0; r < SK; ++r) {
+        if ((uint32_t)r == rank) continue;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 t = ld_dsmem_f4(stg_lane + (uint32_t)((c * 8 + j4) * BM) * 16u, (uint32_t)r);
+          v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
+        }
+      }
+      const int col0 = n0 + c * 32;
+      float* crow = e.C + (long long)row * e.ldc;
+      if (!row_ok || col0 >= p.N) {
+        // tile overhang
+      } else if (vec_ok && col0 + 32 <= p.N) {
+        float rres[32];
+        if (e.R && r_vec_ok) {
+          const float4* rp4 = reinterpret_cast<const float4*>(e.R + (long long)row * e.ldr + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 t = rp4[j]; rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rres[j] = e.R ? e.R[(long long)row * e.ldr + col0 + j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j];
+          if (e.bias) x += __ldg(e.bias + col0 + j);
+          x = espb::apply_act_acc(x, e.act);
+          v[j] = fmaf(e.alpha, x, rres[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o, l;
+          const float t0 = v[j], t1 = v[j + 1], t2 = v[j + 2], t3 = v[j + 3];
+          if (e.split_out) {
+            o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
+            l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
+            *reinterpret_cast<float4*>(crow + col0 + j) = o;
+            *reinterpret_cast<float4*>(crow + e.c_plane + col0 + j) = l;
+          } else {
+            o.x = t0; o.y = t1; o.z = t2; o.w = t3;
+            *reinterpret_cast<float4*>(crow + col0 + j) = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col < p.N) {
+            float t = epi_value(e, v[j], row, col);
+            if (e.split_out) {
+              float h = espb::tf32_hi(t);
+              crow[col] = h; crow[e.c_plane + col] = espb::tf32_lo(t, h);
+            } else {
+              crow[col] = t;
+            }
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all_v();     // peers may still read this CTA's parked partials until all are done
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
   }
@@ -977,6 +1178,30 @@ int launch_tc_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmD
   return ESPB_OK;
 }
 
+template <int BN, int STAGES, int SK>
+int launch_tc_sk(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, cudaStream_t stream) {
+  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * BN * 128) + 1024 + 16 * STAGES + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tf32x3_sk_kernel<BN, STAGES, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      espb_set_error("cudaFuncSetAttribute(max dynamic smem) failed");
+      return ESPB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, SK);
+  gemm_tf32x3_sk_kernel<BN, STAGES, SK><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, d);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+// ESPB_GEMM_SPLITK=0 disables the split-K decode kernels (A/B measurements); read once.
+bool splitk_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ESPB_GEMM_SPLITK"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 }  // namespace
 
 int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version) {
@@ -1011,6 +1236,23 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
     if (rc != ESPB_OK) return rc;
     if (bn == 256) return launch_tc2<256, 3>(tmA, tmB, d, bxm, bym, axm, aym, stream);
     return launch_tc2<128, 4>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+  }
+  if (version == 2 && nb == 1 && d.a_mode == 0 && d.band_t == 0 && d.kob == 0 && d.N > 64 && splitk_enabled()) {
+    // decode-step shapes: split K over a cluster while the whole problem still fits one wave of 1-CTA tiles
+    const long long tiles128 = tiles_m * ((d.N + 127) / 128);
+    const int num_kb = (d.K + BK - 1) / BK;
+    int sk = 0;
+    auto all_ranks_busy = [&](int n) { return (n - 1) * ((num_kb + n - 1) / n) < num_kb; };   // every K slice holds >= 1 k-block
+    if (tiles128 * 4 <= 148 && num_kb >= 8 && all_ranks_busy(4)) sk = 4;
+    else if (tiles128 * 2 <= 148 && num_kb >= 4 && all_ranks_busy(2)) sk = 2;
+    if (sk) {
+      long long dims[5] = {d.K, d.N, 1, 1, 2};
+      long long str[4] = {d.ldb, 0, 0, d.b_plane};
+      rc = make_map(&tmB, d.B, dims, str, 128);
+      if (rc != ESPB_OK) return rc;
+      if (sk == 4) return launch_tc_sk<128, 3, 4>(tmA, tmB, d, stream);
+      return launch_tc_sk<128, 3, 2>(tmA, tmB, d, stream);
+    }
   }
   int bn;
   if (d.N <= 64) bn = 64;
