@@ -5,6 +5,9 @@
 //
 // Reference: espnet2/legacy/nets/pytorch_backend/transformer/{layer_norm,subsampling,attention}.py,
 // .../conformer/{convolution,encoder_layer}.py (line ranges at each kernel).
+#include <stdint.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -188,6 +191,57 @@ __global__ void __launch_bounds__(256) relpos_softmax_kernel(const float* __rest
   }
 }
 
+// Long rows: the combined scores of a row are parked in shared memory (one row per warp), so ac / bd are read from global exactly
+// once and the division / exp run once per element; ac loads and the hi/lo probability stores are 128-bit (lane owns 4 consecutive keys).
+__global__ void __launch_bounds__(256) relpos_softmax_smem_kernel(const float* __restrict__ ac, const float* __restrict__ bd, int B, int H, int T, int Tp,
+                                                                  int Rp, const int* __restrict__ lens, float inv_scale_div,
+                                                                  float* __restrict__ probs, long long probs_plane) {
+  extern __shared__ float sm_rows[];   // [8][Tp]
+  const long long rowid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (rowid >= (long long)B * H * T) return;
+  const int lane = threadIdx.x & 31;
+  float* row = sm_rows + (threadIdx.x >> 5) * Tp;
+  const int i = (int)(rowid % T);
+  const int b = (int)(rowid / ((long long)H * T));
+  const int len = lens[b];
+  const float* ar = ac + rowid * Tp;
+  const float* br = bd + rowid * Rp + (T - 1 - i);
+  float* pr = probs + rowid * Tp;
+  float mx = -INFINITY;
+  for (int j = 4 * lane; j < len; j += 128) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(ar + j));
+    float4 s;
+    s.x = (a.x + __ldg(br + j)) / inv_scale_div;
+    s.y = (j + 1 < len) ? (a.y + __ldg(br + j + 1)) / inv_scale_div : -INFINITY;
+    s.z = (j + 2 < len) ? (a.z + __ldg(br + j + 2)) / inv_scale_div : -INFINITY;
+    s.w = (j + 3 < len) ? (a.w + __ldg(br + j + 3)) / inv_scale_div : -INFINITY;
+    *reinterpret_cast<float4*>(row + j) = s;
+    mx = fmaxf(fmaxf(mx, s.x), fmaxf(fmaxf(s.y, s.z), s.w));
+  }
+  mx = espb::warp_max(mx);
+  float sum = 0.f;
+  for (int j = 4 * lane; j < len; j += 128) {
+    float4 s = *reinterpret_cast<const float4*>(row + j);
+    s.x = expf(s.x - mx);
+    s.y = (j + 1 < len) ? expf(s.y - mx) : 0.f;
+    s.z = (j + 2 < len) ? expf(s.z - mx) : 0.f;
+    s.w = (j + 3 < len) ? expf(s.w - mx) : 0.f;
+    *reinterpret_cast<float4*>(row + j) = s;
+    sum += (s.x + s.y) + (s.z + s.w);
+  }
+  sum = espb::warp_sum(sum);
+  for (int j = 4 * lane; j < Tp; j += 128) {
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < len) e = *reinterpret_cast<const float4*>(row + j);
+    float4 hi, lo;
+    const float p0 = e.x / sum, p1 = e.y / sum, p2 = e.z / sum, p3 = e.w / sum;
+    hi.x = espb::tf32_hi(p0); hi.y = espb::tf32_hi(p1); hi.z = espb::tf32_hi(p2); hi.w = espb::tf32_hi(p3);
+    lo.x = espb::tf32_lo(p0, hi.x); lo.y = espb::tf32_lo(p1, hi.y); lo.z = espb::tf32_lo(p2, hi.z); lo.w = espb::tf32_lo(p3, hi.w);
+    *reinterpret_cast<float4*>(pr + j) = hi;
+    *reinterpret_cast<float4*>(pr + probs_plane + j) = lo;
+  }
+}
+
 // ---------------------------------------------------------------- convolution module (convolution.py:56-79)
 // y [M][2C] = pointwise_conv1 output. GLU -> depthwise conv (K taps, zero pad at the utterance's own ends) ->
 // BatchNorm eval folded to x*bn_a + bn_b -> Swish -> split [M][C].
@@ -296,6 +350,9 @@ int espb_relpos_softmax_f32(const float* ac, const float* bd, int B, int H, int 
   const unsigned grid = (unsigned)((rows + 7) / 8);
   // (a register-resident single-pass variant <NV> measured slower on B200: 3.5 ms vs 2.6 ms at T=937 -- lower occupancy; kept for short rows)
   if (T <= 128) relpos_softmax_kernel<4><<<grid, 256, 0, stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
+  else if ((Tp & 3) == 0 && (probs_plane & 3) == 0 && (reinterpret_cast<uintptr_t>(ac) & 15) == 0 && (reinterpret_cast<uintptr_t>(probs) & 15) == 0 &&
+           (size_t)8 * Tp * sizeof(float) <= 48 * 1024 && !getenv("ESPB_SOFTMAX_3PASS"))
+    relpos_softmax_smem_kernel<<<grid, 256, (size_t)8 * Tp * sizeof(float), stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
   else relpos_softmax_kernel<0><<<grid, 256, 0, stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;

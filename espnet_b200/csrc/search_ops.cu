@@ -260,119 +260,134 @@ __device__ __forceinline__ void mma3_tf32(float (&c)[4], const uint32_t (&ah)[4]
   mma_m16n8k8_tf32(c, ah, bh);
 }
 
+__device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const void* gsrc, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The K tiles and then the V tiles of one (utterance, head) stream through an S-deep cp.async ring of 64-frame tiles (one
+// __syncthreads per tile; S-1 tiles in flight per block, two blocks per SM), so the HBM read of the encoder memory -- the
+// algorithmic cost of this kernel -- is never stalled behind the mma phases; the softmax runs while the first V tiles land.
+template <int S>
 __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* __restrict__ q, const float* __restrict__ kmem, const float* __restrict__ vmem,
                                                                   int Tmax, const int* __restrict__ lens, int W, int D, int H,
                                                                   float* __restrict__ ctx, long long ctx_plane, int w0, int Wall) {
-  constexpr int DK = 64, QST = 68, KST = 68, VST = 72;
-  extern __shared__ float sm[];  // q [16][68] | scores [W][Tmax] (pad 4; reused for the cross-warp reduction) | tile [128][72]
+  constexpr int DK = 64, QST = 68, KST = 68, VST = 72, TR = 64, TILE_F = TR * VST;
+  extern __shared__ float sm[];  // q [16][68] | scores [W][Tmax] (pad 4) | ring [S][64][72] (reused for the cross-warp reduction)
   const int u = blockIdx.x / H, h = blockIdx.x % H;
   const int T = lens[u];
   float* qs = sm;
   float* sc = qs + 16 * QST;
-  float* tile = sc + (((long long)W * Tmax + 3) & ~3LL);
+  float* ring = sc + (((long long)W * Tmax + 3) & ~3LL);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
+  const float4* kb = reinterpret_cast<const float4*>(kmem + ((long long)(u * H + h) * Tmax) * DK);
+  const float4* vb = reinterpret_cast<const float4*>(vmem + ((long long)(u * H + h) * Tmax) * DK);
+  const int nt = (T + TR - 1) / TR, NT = 2 * nt;
+  auto issue = [&](int i) {
+    if (i < NT) {
+      const bool isk = i < nt;
+      const int tb = (isk ? i : i - nt) * TR;
+      const float4* src = isk ? kb : vb;
+      const int st = isk ? KST : VST;
+      float* dst = ring + (i % S) * TILE_F;
+#pragma unroll
+      for (int j = threadIdx.x; j < TR * 16; j += 256) {
+        const int rr = j >> 4, cc = j & 15;
+        const bool ok = tb + rr < T;      // frames past the utterance are zero-filled (src-size 0)
+        cp_async16_zfill(dst + rr * st + cc * 4, src + (ok ? (long long)(tb + rr) * 16 + cc : 0), ok ? 16 : 0);
+      }
+    }
+    cp_async_commit();                    // one (possibly empty) group per tile index keeps the wait_group arithmetic uniform
+  };
+#pragma unroll
+  for (int i = 0; i < S - 1; ++i) issue(i);
   for (int i = threadIdx.x; i < 16 * DK; i += blockDim.x) {
     const int w = i / DK, d = i % DK;
     qs[w * QST + d] = (w < W) ? q[((long long)(u * Wall + w0 + w)) * D + h * DK + d] : 0.f;
   }
-  const float4* kb = reinterpret_cast<const float4*>(kmem + ((long long)(u * H + h) * Tmax) * DK);
-  const float4* vb = reinterpret_cast<const float4*>(vmem + ((long long)(u * H + h) * Tmax) * DK);
   const float rs = 8.0f;   // sqrt(d_k)
-  __syncthreads();
-  // ---- scores: A = K tile rows (16 per warp), B = Q^T (two n-tiles of 8 slots), K-dim = d
-  for (int tb = 0; tb < T; tb += 128) {
-    const int rows = min(128, T - tb);
-    for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
-      const int rr = i >> 4, cc = i & 15;
-      const float4 v = (rr < rows) ? __ldg(kb + (long long)(tb + rr) * 16 + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(tile + rr * KST + cc * 4) = v;
-    }
-    __syncthreads();
-    const int r0 = warp * 16;
-    if (r0 < rows) {
-      float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const int k0 = ks * 8;
-        uint32_t ah[4], al[4];
-        split_tf32(tile[(r0 + g) * KST + k0 + t4], ah[0], al[0]);
-        split_tf32(tile[(r0 + g + 8) * KST + k0 + t4], ah[1], al[1]);
-        split_tf32(tile[(r0 + g) * KST + k0 + t4 + 4], ah[2], al[2]);
-        split_tf32(tile[(r0 + g + 8) * KST + k0 + t4 + 4], ah[3], al[3]);
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          uint32_t bh[2], bl[2];
-          split_tf32(qs[(nt * 8 + g) * QST + k0 + t4], bh[0], bl[0]);
-          split_tf32(qs[(nt * 8 + g) * QST + k0 + t4 + 4], bh[1], bl[1]);
-          mma3_tf32(c[nt], ah, al, bh, bl);
-        }
-      }
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int s0 = nt * 8 + 2 * t4;
-        const int ta = tb + r0 + g, tbb = ta + 8;
-        if (s0 < W) { if (ta < T) sc[s0 * Tmax + ta] = c[nt][0] / rs; if (tbb < T) sc[s0 * Tmax + tbb] = c[nt][2] / rs; }
-        if (s0 + 1 < W) { if (ta < T) sc[(s0 + 1) * Tmax + ta] = c[nt][1] / rs; if (tbb < T) sc[(s0 + 1) * Tmax + tbb] = c[nt][3] / rs; }
-      }
-    }
-    __syncthreads();
-  }
-  // ---- softmax over t per slot (no memory mask: batch_score passes none, transformer_decoder.py:294-303)
-  for (int w = warp; w < W; w += 8) {
-    float* r = sc + w * Tmax;
-    float mx = -INFINITY;
-    for (int t = lane; t < T; t += 32) mx = fmaxf(mx, r[t]);
-    mx = espb::warp_max(mx);
-    float sum = 0.f;
-    for (int t = lane; t < T; t += 32) { float e = expf(r[t] - mx); r[t] = e; sum += e; }
-    sum = espb::warp_sum(sum);
-    for (int t = lane; t < T; t += 32) r[t] = r[t] / sum;
-  }
-  __syncthreads();
-  // ---- context: A = P (16 slot rows, clamped to W-1), B = V tile, K-dim = t (each warp takes two 8-frame k-steps per 128-frame tile)
   float acc[8][4];
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
+  for (int n8 = 0; n8 < 8; ++n8) { acc[n8][0] = 0.f; acc[n8][1] = 0.f; acc[n8][2] = 0.f; acc[n8][3] = 0.f; }
   const int sa = min(g, W - 1), sb = min(g + 8, W - 1);
-  for (int tb = 0; tb < T; tb += 128) {
-    const int rows = min(128, T - tb);
-    for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
-      const int rr = i >> 4, cc = i & 15;
-      const float4 v = (rr < rows) ? __ldg(vb + (long long)(tb + rr) * 16 + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(tile + rr * VST + cc * 4) = v;
+
+  for (int i = 0; i < NT; ++i) {
+    cp_async_wait<S - 2>();               // this thread's copies of tile i have landed ...
+    __syncthreads();                      // ... and everyone's; all warps are done with tile i-1, whose slot is refilled next
+    issue(i + S - 1);
+    if (i == nt) {
+      // ---- softmax over t per slot (no memory mask: batch_score passes none, transformer_decoder.py:294-303)
+      for (int w = warp; w < W; w += 8) {
+        float* r = sc + w * Tmax;
+        float mx = -INFINITY;
+        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, r[t]);
+        mx = espb::warp_max(mx);
+        float sum = 0.f;
+        for (int t = lane; t < T; t += 32) { float e = expf(r[t] - mx); r[t] = e; sum += e; }
+        sum = espb::warp_sum(sum);
+        for (int t = lane; t < T; t += 32) r[t] = r[t] / sum;
+      }
+      __syncthreads();
     }
-    __syncthreads();
+    const float* tile = ring + (i % S) * TILE_F;
+    if (i < nt) {
+      // ---- scores: A = K tile rows (16 per warp quarter), B = Q^T (n-tile of 8 slots per warp half), K-dim = d
+      const int tb = i * TR, rows = min(TR, T - tb);
+      const int r0 = (warp & 3) * 16, nb = warp >> 2;
+      if (r0 < rows && nb * 8 < W) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      const int ks = warp + kk * 8;
-      if (ks * 8 < rows) {
-        const int t0 = tb + ks * 8 + t4, t1 = t0 + 4;
+        for (int ks = 0; ks < 8; ++ks) {
+          const int k0 = ks * 8;
+          uint32_t ah[4], al[4], bh[2], bl[2];
+          split_tf32(tile[(r0 + g) * KST + k0 + t4], ah[0], al[0]);
+          split_tf32(tile[(r0 + g + 8) * KST + k0 + t4], ah[1], al[1]);
+          split_tf32(tile[(r0 + g) * KST + k0 + t4 + 4], ah[2], al[2]);
+          split_tf32(tile[(r0 + g + 8) * KST + k0 + t4 + 4], ah[3], al[3]);
+          split_tf32(qs[(nb * 8 + g) * QST + k0 + t4], bh[0], bl[0]);
+          split_tf32(qs[(nb * 8 + g) * QST + k0 + t4 + 4], bh[1], bl[1]);
+          mma3_tf32(c, ah, al, bh, bl);
+        }
+        const int s0 = nb * 8 + 2 * t4;
+        const int ta = tb + r0 + g, tbb = ta + 8;
+        if (s0 < W) { if (ta < T) sc[s0 * Tmax + ta] = c[0] / rs; if (tbb < T) sc[s0 * Tmax + tbb] = c[2] / rs; }
+        if (s0 + 1 < W) { if (ta < T) sc[(s0 + 1) * Tmax + ta] = c[1] / rs; if (tbb < T) sc[(s0 + 1) * Tmax + tbb] = c[3] / rs; }
+      }
+    } else {
+      // ---- context: A = P (16 slot rows, clamped to W-1), B = V tile, K-dim = t (warp w takes the 8-frame k-step w of the tile)
+      const int tb = (i - nt) * TR, rows = min(TR, T - tb);
+      if (warp * 8 < rows) {
+        const int t0 = tb + warp * 8 + t4, t1 = t0 + 4;
         uint32_t ah[4], al[4];
         split_tf32(t0 < T ? sc[sa * Tmax + t0] : 0.f, ah[0], al[0]);
         split_tf32(t0 < T ? sc[sb * Tmax + t0] : 0.f, ah[1], al[1]);
         split_tf32(t1 < T ? sc[sa * Tmax + t1] : 0.f, ah[2], al[2]);
         split_tf32(t1 < T ? sc[sb * Tmax + t1] : 0.f, ah[3], al[3]);
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int n8 = 0; n8 < 8; ++n8) {
           uint32_t bh[2], bl[2];
-          split_tf32(tile[(ks * 8 + t4) * VST + nt * 8 + g], bh[0], bl[0]);
-          split_tf32(tile[(ks * 8 + t4 + 4) * VST + nt * 8 + g], bh[1], bl[1]);
-          mma3_tf32(acc[nt], ah, al, bh, bl);
+          split_tf32(tile[(warp * 8 + t4) * VST + n8 * 8 + g], bh[0], bl[0]);
+          split_tf32(tile[(warp * 8 + t4 + 4) * VST + n8 * 8 + g], bh[1], bl[1]);
+          mma3_tf32(acc[n8], ah, al, bh, bl);
         }
       }
     }
-    __syncthreads();
   }
-  // ---- cross-warp reduction: red[warp][slot 16][d 64] in the (dead) score / tile area, then split store of the W valid slots
-  float* red = sc;   // needs 8*16*64 floats = 32 KB <= scores + tile area (tile alone is 36 KB)
-  if (((long long)W * Tmax + 3) / 4 * 4 + 128 * VST < 8 * 16 * DK) red = tile;   // never true for the shapes we launch; keeps the intent explicit
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- cross-warp reduction: red[warp][slot 16][d 64] (32 KB) in the ring, then split store of the W valid slots
+  float* red = ring;
+  static_assert(S * TILE_F >= 8 * 16 * DK, "reduction scratch must fit in the ring");
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    float* r0p = red + ((long long)warp * 16 + g) * DK + nt * 8 + 2 * t4;
-    float* r1p = red + ((long long)warp * 16 + g + 8) * DK + nt * 8 + 2 * t4;
-    r0p[0] = acc[nt][0]; r0p[1] = acc[nt][1];
-    r1p[0] = acc[nt][2]; r1p[1] = acc[nt][3];
+  for (int n8 = 0; n8 < 8; ++n8) {
+    float* r0p = red + ((long long)warp * 16 + g) * DK + n8 * 8 + 2 * t4;
+    float* r1p = red + ((long long)warp * 16 + g + 8) * DK + n8 * 8 + 2 * t4;
+    r0p[0] = acc[n8][0]; r0p[1] = acc[n8][1];
+    r1p[0] = acc[n8][2]; r1p[1] = acc[n8][3];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < W * DK; i += blockDim.x) {
@@ -756,16 +771,22 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
     const int Wg = (W - w0 < 16) ? W - w0 : 16;
     if (dk == 64 && !getenv("ESPNET_B200_SRC_ATTN_FFMA")) {
       const size_t scs4 = ((size_t)Wg * Tmax + 3) & ~(size_t)3;
-      const size_t need = (16 * 68 + scs4 + 128 * 72) * sizeof(float);
-      if (need <= 200 * 1024) {
-        static bool attr = false;
-        if (!attr) {
-          if (cudaFuncSetAttribute(dec_src_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
+      const size_t fixed = (16 * 68 + scs4) * sizeof(float), tile_b = 64 * 72 * sizeof(float);
+      // deepest ring that still lets two blocks share an SM (227 KB), else the deepest that fits one block
+      int S = 0;
+      for (int cand = 4; cand >= 2 && !S; --cand) if (fixed + cand * tile_b <= 113 * 1024) S = cand;
+      for (int cand = 4; cand >= 2 && !S; --cand) if (fixed + cand * tile_b <= 200 * 1024) S = cand;
+      if (S) {
+        using MmaFn = void (*)(const float*, const float*, const float*, int, const int*, int, int, int, float*, long long, int, int);
+        const MmaFn fn = (S == 4) ? dec_src_attn_mma_kernel<4> : (S == 3) ? dec_src_attn_mma_kernel<3> : dec_src_attn_mma_kernel<2>;
+        static bool attr[5] = {false, false, false, false, false};
+        if (!attr[S]) {
+          if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess) {
             espb_set_error("dec_src_attn: cannot raise dynamic shared memory"); return ESPB_ERR_CUDA;
           }
-          attr = true;
+          attr[S] = true;
         }
-        dec_src_attn_mma_kernel<<<U * H, 256, need, stream>>>(q, kmem, vmem, Tmax, lens, Wg, D, H, ctx, ctx_plane, w0, W);
+        fn<<<U * H, 256, fixed + S * tile_b, stream>>>(q, kmem, vmem, Tmax, lens, Wg, D, H, ctx, ctx_plane, w0, W);
         ESPB_CHECK_LAUNCH();
         continue;
       }

@@ -1,0 +1,60 @@
+"""Stand-alone timing of single hot kernels on bench-shaped synthetic data (CUDA events, L2 flushed between launches).
+
+    python scripts/kernel_microbench.py softmax|srcattn|selfattn|all [reps]
+
+Also the target for one-kernel ncu captures (scripts/gpu_ncu_micro.sh): a 5000-launch bench step under ncu is expensive,
+one launch of one kernel is not.
+"""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from espnet_b200.lib import call, ptr  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+dev = "cuda"
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(name, fn, bytes_alg):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    us = ts[len(ts) // 2]
+    print(f"[kernel_microbench] {name}: median {us:9.1f} us  min {ts[0]:9.1f} us   algorithmic {bytes_alg / 1e6:8.1f} MB -> {bytes_alg / us / 1e6:6.2f} TB/s")
+
+
+if which in ("softmax", "all"):
+    B, H, T = 64, 8, 937
+    Tp, Rp = 960, 1888
+    ac = torch.randn(B * H * T, Tp, device=dev)
+    bd = torch.randn(B * H * T, Rp, device=dev)
+    probs = torch.empty(2, B * H * T, Tp, device=dev)
+    lens = torch.full((B,), T, dtype=torch.int32, device=dev)
+    alg = B * H * T * (2 * T + 2 * Tp) * 4
+    timeit("relpos_softmax B64 H8 T937", lambda: call("espb_relpos_softmax_f32", ptr(ac), ptr(bd), B, H, T, Tp, Rp, ptr(lens), math.sqrt(64.0), ptr(probs),
+                                                      B * H * T * Tp), alg)
+    del ac, bd, probs
+
+if which in ("srcattn", "all"):
+    U, H, T, W, D = 64, 8, 937, 10, 512
+    n = U * W
+    q = torch.randn(n, D, device=dev)
+    kv = torch.randn(2, U, H, T, 64, device=dev)
+    ctx = torch.empty(2, n, D, device=dev)
+    lens = torch.full((U,), T, dtype=torch.int32, device=dev)
+    alg = 2 * U * H * T * 64 * 4
+    timeit("dec_src_attn U64 H8 T937 W10", lambda: call("espb_dec_src_attn_f32", ptr(q), ptr(kv[0]), ptr(kv[1]), U, T, ptr(lens), W, D, H, ptr(ctx), n * D), alg)

@@ -121,7 +121,7 @@ def test_encoder_batch_and_ragged_vs_oracle(gemm_mode):
     w = random_weights(cfg, seed=5)
     s2t = speech2text(cfg, w, beam_size=2, ctc_weight=0.3)
     o = oracle.OracleSpeech2Text(cfg, w, beam_size=2, ctc_weight=0.3)
-    for lens in ([24000] * 3, [40000, 17000, 29000, 8000]):
+    for lens in ([24000] * 3, [40000, 17000, 29000, 8000], [96000, 51000, 70001]):   # the last: rows longer than 128 keys (smem softmax), ragged
         waves = [refbuild.waveform(50 + i, n) for i, n in enumerate(lens)]
         speech, sl = s2t._to_batch(waves)
         enc, elens = s2t.asr_model.encode(speech, sl)
