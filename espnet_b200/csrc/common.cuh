@@ -20,6 +20,27 @@ namespace espb {
 
 constexpr int ACT_NONE = 0, ACT_RELU = 1, ACT_SWISH = 2;
 
+// Programmatic dependent launch for the launch-latency-bound decode step (one beam-search step is ~80 small dependent kernels).
+// A kernel launched through launch_pdl may become resident while its stream predecessor still runs; it must execute pdl_wait()
+// before its first global-memory access (setup that touches only shared memory / TMEM / barriers may precede it).  pdl_trigger()
+// lets the next kernel in the stream do the same.  Every kernel of the chain waits before it completes, so completion order --
+// and with it every read-after-write / write-after-read dependency of plain stream order -- is preserved transitively.
+// ESPB_PDL=0 launches with full stream serialisation; griddepcontrol.* are no-ops then.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // 3xTF32 operand split: hi keeps the top 19 bits (sign, 8 exp, 10 mantissa) of the fp32 value,
 // lo = x - hi is exactly representable in fp32; both planes are stored as fp32 words whose low
 // 13 bits are zero, so tcgen05 kind::tf32 consumes them without rounding ambiguity.

@@ -7,6 +7,8 @@ namespace {
 
 // In-place log-softmax of each row of x [rows][V] (row pitch ld). One block per row.
 __global__ void __launch_bounds__(256) log_softmax_rows_kernel(float* __restrict__ x, long long ld, int V) {
+  espb::pdl_trigger();
+  espb::pdl_wait();
   __shared__ float red[33];
   float* r = x + (long long)blockIdx.x * ld;
   float mx = -INFINITY;
@@ -67,7 +69,7 @@ extern "C" {
 
 int espb_log_softmax_rows_f32(float* x, long long rows, long long ld, int V, cudaStream_t stream) {
   if (rows <= 0) return ESPB_OK;
-  log_softmax_rows_kernel<<<(unsigned)rows, 256, 0, stream>>>(x, ld, V);
+  espb::launch_pdl(log_softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, stream, x, ld, V);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

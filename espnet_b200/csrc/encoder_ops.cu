@@ -27,6 +27,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int D, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, float* __restrict__ out_plain,
                                                         float* __restrict__ out_split, long long split_plane) {
+  espb::pdl_trigger();
+  espb::pdl_wait();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -303,10 +305,10 @@ int espb_layernorm_f32(const float* x, long long rows, int D, const float* gamma
   if (D > 2048 || D <= 0) { espb_set_error("layernorm: D must be in (0, 2048]"); return ESPB_ERR_ARG; }
   if (rows <= 0) return ESPB_OK;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (D <= 256) layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
-  else if (D <= 512) layernorm_kernel<16><<<grid, 256, 0, stream>>>(x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
-  else if (D <= 1024) layernorm_kernel<32><<<grid, 256, 0, stream>>>(x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
-  else layernorm_kernel<64><<<grid, 256, 0, stream>>>(x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+  if (D <= 256) espb::launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), 0, stream, x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+  else if (D <= 512) espb::launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(256), 0, stream, x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+  else if (D <= 1024) espb::launch_pdl(layernorm_kernel<32>, dim3(grid), dim3(256), 0, stream, x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+  else espb::launch_pdl(layernorm_kernel<64>, dim3(grid), dim3(256), 0, stream, x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

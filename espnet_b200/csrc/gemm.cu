@@ -121,7 +121,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int bx = blockIdx.z % p.nbx, by = blockIdx.z / p.nbx;
   const int num_kb = (p.K + BK - 1) / BK;
-  if (p.band_t > 0 && ((n0 + BN - 1 < p.band_t - 1 - (m0 + BM - 1)) || (n0 > 2 * p.band_t - 2 - m0))) return;   // tile outside the rel-pos band
+  if (p.band_t > 0 && ((n0 + BN - 1 < p.band_t - 1 - (m0 + BM - 1)) || (n0 > 2 * p.band_t - 2 - m0))) {   // tile outside the rel-pos band
+    espb::pdl_wait();
+    return;
+  }
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
@@ -138,6 +141,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  espb::pdl_trigger();   // barriers, TMEM and descriptors are ready: the next kernel may start its own setup
+  espb::pdl_wait();      // first global access (TMA loads of A / B) follows
 
   if (warp == 0) {
     if (lane == 0) {
@@ -323,6 +328,8 @@ gemm_tf32x3_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   cluster_sync_all_v();     // every CTA's barriers are initialised before any multicast / remote arrive can reach them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  espb::pdl_trigger();
+  espb::pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -503,6 +510,8 @@ gemm_tf32x3_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  espb::pdl_trigger();
+  espb::pdl_wait();
   const int q = warp & 3;                                // TMEM lane quarter of an epilogue warp
   // staging layout: [chunk][j/4][row 0..127][4 floats] -> 128-bit conflict-free writes (lane = row) and 128-bit remote reads
   const uint32_t stg_lane = smem_base + (uint32_t)(q * 32 + lane) * 16u;
@@ -1118,8 +1127,9 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc
     attr_set = true;
   }
   dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.nbx * d.nby);
-  gemm_tf32x3_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
-  ESPB_CHECK_LAUNCH();
+  if (espb::launch_pdl(gemm_tf32x3_kernel<BN, STAGES>, grid, dim3(NUM_THREADS), smem, stream, tmA, tmB, d, bxm, bym, axm, aym) != cudaSuccess) {
+    espb_set_error(cudaGetErrorString(cudaGetLastError())); return ESPB_ERR_CUDA;
+  }
   return ESPB_OK;
 }
 
@@ -1173,8 +1183,9 @@ int launch_tc_mc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmD
     attr_set = true;
   }
   dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, d.nbx * d.nby);
-  gemm_tf32x3_mc_kernel<BN, STAGES, MC><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
-  ESPB_CHECK_LAUNCH();
+  if (espb::launch_pdl(gemm_tf32x3_mc_kernel<BN, STAGES, MC>, grid, dim3(NUM_THREADS), smem, stream, tmA, tmB, d, bxm, bym, axm, aym) != cudaSuccess) {
+    espb_set_error(cudaGetErrorString(cudaGetLastError())); return ESPB_ERR_CUDA;
+  }
   return ESPB_OK;
 }
 
@@ -1190,8 +1201,9 @@ int launch_tc_sk(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmD
     attr_set = true;
   }
   dim3 grid((d.M + BM - 1) / BM, (d.N + BN - 1) / BN, SK);
-  gemm_tf32x3_sk_kernel<BN, STAGES, SK><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, d);
-  ESPB_CHECK_LAUNCH();
+  if (espb::launch_pdl(gemm_tf32x3_sk_kernel<BN, STAGES, SK>, grid, dim3(NUM_THREADS), smem, stream, tmA, tmB, d) != cudaSuccess) {
+    espb_set_error(cudaGetErrorString(cudaGetLastError())); return ESPB_ERR_CUDA;
+  }
   return ESPB_OK;
 }
 

@@ -25,6 +25,8 @@ __device__ __forceinline__ void store_split(float* p, long long plane, float v) 
 // ---------------------------------------------------------------- decoder input: embed(last token)*sqrt(D) + PE[pos]
 __global__ void dec_embed_kernel(const int* __restrict__ last_tok, const float* __restrict__ emb, const float* __restrict__ pe, int pos,
                                  const int* __restrict__ step_ptr, int D, float scale, float* __restrict__ x) {
+  espb::pdl_trigger();
+  espb::pdl_wait();
   if (step_ptr) pos += *step_ptr;
   const int s = blockIdx.x;
   const float* e = emb + (long long)last_tok[s] * D;
@@ -41,6 +43,8 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
                                                             const int* __restrict__ step_ptr, int sc_ld, float* __restrict__ ctx,
                                                             long long ctx_plane) {
   extern __shared__ float sm[];  // per warp: sc_ld >= pos+1 scores
+  espb::pdl_trigger();
+  espb::pdl_wait();
   if (step_ptr) pos += *step_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wid = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -111,6 +115,99 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const float* __restr
   }
 }
 
+// d_k = 64 instance: a half-warp covers one 256-byte K / V row with 128-bit loads, so every load instruction fetches two prefix
+// positions; ancestor slots of 32 positions are read with one coalesced load and broadcast by shuffle (no dependent
+// index -> row load chain); dot products reduce over 16 lanes.
+__global__ void __launch_bounds__(128) dec_self_attn64_kernel(const float* __restrict__ qkv, float* __restrict__ kc, float* __restrict__ vc,
+                                                              const int* __restrict__ anc, int anc_ld, int n, int D, int H, int pos,
+                                                              const int* __restrict__ step_ptr, int sc_ld, float* __restrict__ ctx,
+                                                              long long ctx_plane) {
+  extern __shared__ float sm[];  // per warp: sc_ld >= pos+1 scores
+  espb::pdl_trigger();
+  espb::pdl_wait();
+  if (step_ptr) pos += *step_ptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (wid >= n * H) return;
+  const int s = wid / H, h = wid % H;
+  const int half = lane >> 4, l16 = lane & 15;
+  float* sc = sm + warp * sc_ld;
+  const float* q = qkv + (long long)s * 3 * D + h * 64 + 4 * l16;
+  const float4 q4 = *reinterpret_cast<const float4*>(q);
+  const float4 kn = *reinterpret_cast<const float4*>(q + D);
+  const float4 vn = *reinterpret_cast<const float4*>(q + 2 * D);
+  if (half == 0) {   // append this step's k, v to the cache
+    *reinterpret_cast<float4*>(kc + ((long long)pos * n + s) * D + h * 64 + 4 * l16) = kn;
+    *reinterpret_cast<float4*>(vc + ((long long)pos * n + s) * D + h * 64 + 4 * l16) = vn;
+  }
+  const int* an = anc + (long long)s * anc_ld;
+  const long long hoff = (long long)h * 64 + 4 * l16;
+  for (int j0 = 0; j0 <= pos; j0 += 32) {
+    const int my_a = (j0 + lane < pos) ? an[j0 + lane] : 0;
+#pragma unroll
+    for (int it0 = 0; it0 < 16; it0 += 8) {
+      if (j0 + 2 * it0 > pos) break;          // warp-uniform
+      float part[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int jj = 2 * (it0 + u) + half, j = j0 + jj;
+        const int aj = __shfl_sync(0xffffffffu, my_a, jj);
+        float a = 0.f;
+        if (j < pos) {
+          const float4 k4 = *reinterpret_cast<const float4*>(kc + ((long long)j * n + aj) * D + hoff);
+          a = fmaf(q4.x, k4.x, fmaf(q4.y, k4.y, fmaf(q4.z, k4.z, q4.w * k4.w)));
+        } else if (j == pos) {
+          a = fmaf(q4.x, kn.x, fmaf(q4.y, kn.y, fmaf(q4.z, kn.z, q4.w * kn.w)));
+        }
+        part[u] = a;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float a = part[u];
+        a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 4);
+        a += __shfl_xor_sync(0xffffffffu, a, 2); a += __shfl_xor_sync(0xffffffffu, a, 1);
+        const int j = j0 + 2 * (it0 + u) + half;
+        if (l16 == 0 && j <= pos) sc[j] = a / 8.0f;
+      }
+    }
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = lane; j <= pos; j += 32) mx = fmaxf(mx, sc[j]);
+  mx = espb::warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j <= pos; j += 32) { float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+  sum = espb::warp_sum(sum);
+  __syncwarp();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j0 = 0; j0 < pos; j0 += 32) {
+    const int my_a = (j0 + lane < pos) ? an[j0 + lane] : 0;
+#pragma unroll 8
+    for (int it = 0; it < 16; ++it) {
+      const int jj = 2 * it + half, j = j0 + jj;
+      if (j0 + 2 * it >= pos) break;          // warp-uniform
+      const int aj = __shfl_sync(0xffffffffu, my_a, jj);
+      if (j < pos) {
+        const float pj = sc[j] / sum;
+        const float4 v4 = *reinterpret_cast<const float4*>(vc + ((long long)j * n + aj) * D + hoff);
+        acc.x = fmaf(pj, v4.x, acc.x); acc.y = fmaf(pj, v4.y, acc.y); acc.z = fmaf(pj, v4.z, acc.z); acc.w = fmaf(pj, v4.w, acc.w);
+      }
+    }
+  }
+  acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+  acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+  if (half == 0) {
+    const float pj = sc[pos] / sum;
+    acc.x = fmaf(pj, vn.x, acc.x); acc.y = fmaf(pj, vn.y, acc.y); acc.z = fmaf(pj, vn.z, acc.z); acc.w = fmaf(pj, vn.w, acc.w);
+    float4 hi, lo;
+    hi.x = espb::tf32_hi(acc.x); hi.y = espb::tf32_hi(acc.y); hi.z = espb::tf32_hi(acc.z); hi.w = espb::tf32_hi(acc.w);
+    lo.x = espb::tf32_lo(acc.x, hi.x); lo.y = espb::tf32_lo(acc.y, hi.y); lo.z = espb::tf32_lo(acc.z, hi.z); lo.w = espb::tf32_lo(acc.w, hi.w);
+    float* o = ctx + (long long)s * D + hoff;
+    *reinterpret_cast<float4*>(o) = hi;
+    *reinterpret_cast<float4*>(o + ctx_plane) = lo;
+  }
+}
+
 // ---------------------------------------------------------------- cross-attention of W queries per utterance over the encoder memory
 // q [n][D]; memory K / V blocks are contiguous per (utterance, head): kmem/vmem + ((u*H + h)*Tmax + t)*dk + d  (written once per
 // utterance by the K/V projection GEMMs and shared by the whole beam).  One block per (utterance, head): the K and V blocks are
@@ -121,6 +218,8 @@ __global__ void __launch_bounds__(256, 3) dec_src_attn_kernel(const float* __res
                                                            int Tmax, const int* __restrict__ lens, int W_rt, int D, int H, int lpr_rt /* pow2 >= dk/4 */,
                                                            float* __restrict__ ctx, long long ctx_plane, int w0, int Wall) {
   extern __shared__ float sm[];  // q [W][dk] | scores [W][Tmax] (reused for the cross-warp PV reduction) | K tile [128][dk+4]
+  espb::pdl_trigger();
+  espb::pdl_wait();
   constexpr bool CT = (WC > 0);
   constexpr int JMAX = CT ? (WC + 1) / 2 : 8;          // beam slots per half block
   constexpr bool FULL = CT && (WC % 2 == 0);           // both halves own exactly JMAX slots
@@ -277,6 +376,8 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* _
                                                                   float* __restrict__ ctx, long long ctx_plane, int w0, int Wall) {
   constexpr int DK = 64, QST = 68, KST = 68, VST = 72, TR = 64, TILE_F = TR * VST;
   extern __shared__ float sm[];  // q [16][68] | scores [W][Tmax] (pad 4) | ring [S][64][72] (reused for the cross-warp reduction)
+  espb::pdl_trigger();
+  espb::pdl_wait();
   const int u = blockIdx.x / H, h = blockIdx.x % H;
   const int T = lens[u];
   float* qs = sm;
@@ -339,7 +440,8 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* _
       const int tb = i * TR, rows = min(TR, T - tb);
       const int r0 = (warp & 3) * 16, nb = warp >> 2;
       if (r0 < rows && nb * 8 < W) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        // one accumulator per product term: three independent 8-deep mma chains instead of one 24-deep chain
+        float c[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const int k0 = ks * 8;
@@ -350,8 +452,12 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* _
           split_tf32(tile[(r0 + g + 8) * KST + k0 + t4 + 4], ah[3], al[3]);
           split_tf32(qs[(nb * 8 + g) * QST + k0 + t4], bh[0], bl[0]);
           split_tf32(qs[(nb * 8 + g) * QST + k0 + t4 + 4], bh[1], bl[1]);
-          mma3_tf32(c, ah, al, bh, bl);
+          mma_m16n8k8_tf32(c1, al, bh);
+          mma_m16n8k8_tf32(c2, ah, bl);
+          mma_m16n8k8_tf32(c, ah, bh);
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[e] += c1[e] + c2[e];   // small terms combined first
         const int s0 = nb * 8 + 2 * t4;
         const int ta = tb + r0 + g, tbb = ta + 8;
         if (s0 < W) { if (ta < T) sc[s0 * Tmax + ta] = c[0] / rs; if (tbb < T) sc[s0 * Tmax + tbb] = c[2] / rs; }
@@ -744,7 +850,7 @@ extern "C" {
 
 int espb_dec_embed_f32(const int* last_tok, const float* emb, const float* pe, int pos, const int* step_ptr, int n, int D, float scale, float* x,
                        cudaStream_t stream) {
-  dec_embed_kernel<<<n, 128, 0, stream>>>(last_tok, emb, pe, pos, step_ptr, D, scale, x);
+  espb::launch_pdl(dec_embed_kernel, dim3(n), dim3(128), 0, stream, last_tok, emb, pe, pos, step_ptr, D, scale, x);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
@@ -755,8 +861,14 @@ int espb_dec_self_attn_f32(const float* qkv, float* kc, float* vc, const int* an
   const int sc_ld = (step_ptr ? max_pos : pos) + 1;   // with a device-side step the score buffer is sized for the longest prefix
   const size_t smem = (size_t)warps * sc_ld * sizeof(float);
   if (smem > 48 * 1024) { espb_set_error("dec_self_attn: prefix too long for the score buffer"); return ESPB_ERR_ARG; }
-  dec_self_attn_kernel<<<(n * H + warps - 1) / warps, warps * 32, smem, stream>>>(qkv, kc, vc, anc, anc_ld, n, D, H, pos, step_ptr, sc_ld, ctx,
-                                                                                  ctx_plane);
+  const bool fast64 = (D / H == 64) && (D % 4 == 0) && (ctx_plane % 4 == 0) && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(kc) |
+                       reinterpret_cast<uintptr_t>(vc) | reinterpret_cast<uintptr_t>(ctx)) & 15) == 0 && !getenv("ESPB_SELF_ATTN_GENERIC");
+  if (fast64)
+    espb::launch_pdl(dec_self_attn64_kernel, dim3((n * H + warps - 1) / warps), dim3(warps * 32), smem, stream, qkv, kc, vc, anc, anc_ld, n, D, H, pos,
+                     step_ptr, sc_ld, ctx, ctx_plane);
+  else
+    espb::launch_pdl(dec_self_attn_kernel, dim3((n * H + warps - 1) / warps), dim3(warps * 32), smem, stream, qkv, kc, vc, anc, anc_ld, n, D, H, pos,
+                     step_ptr, sc_ld, ctx, ctx_plane);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
@@ -786,7 +898,7 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
           }
           attr[S] = true;
         }
-        fn<<<U * H, 256, fixed + S * tile_b, stream>>>(q, kmem, vmem, Tmax, lens, Wg, D, H, ctx, ctx_plane, w0, W);
+        espb::launch_pdl(fn, dim3(U * H), dim3(256), fixed + S * tile_b, stream, q, kmem, vmem, Tmax, lens, Wg, D, H, ctx, ctx_plane, w0, W);
         ESPB_CHECK_LAUNCH();
         continue;
       }
@@ -811,7 +923,7 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
         espb_set_error("dec_src_attn: cannot raise dynamic shared memory"); return ESPB_ERR_CUDA;
       }
     }
-    fn<<<U * H, 256, smem, stream>>>(q, kmem, vmem, Tmax, lens, Wg, D, H, lpr, ctx, ctx_plane, w0, W);
+    espb::launch_pdl(fn, dim3(U * H), dim3(256), smem, stream, q, kmem, vmem, Tmax, lens, Wg, D, H, lpr, ctx, ctx_plane, w0, W);
     ESPB_CHECK_LAUNCH();
   }
   return ESPB_OK;

@@ -58,3 +58,20 @@ if which in ("srcattn", "all"):
     lens = torch.full((U,), T, dtype=torch.int32, device=dev)
     alg = 2 * U * H * T * 64 * 4
     timeit("dec_src_attn U64 H8 T937 W10", lambda: call("espb_dec_src_attn_f32", ptr(q), ptr(kv[0]), ptr(kv[1]), U, T, ptr(lens), W, D, H, ptr(ctx), n * D), alg)
+
+if which in ("selfattn", "all"):
+    U, W, H, D, L = 64, 10, 8, 512, 64
+    n = U * W
+    pos = 40
+    qkv = torch.randn(n, 3 * D, device=dev)
+    kc, vc = torch.randn(L, n, D, device=dev), torch.randn(L, n, D, device=dev)
+    # ancestors stay inside the utterance's beam; older positions collapse onto few slots like a real beam
+    g = torch.Generator(device="cpu").manual_seed(0)
+    anc = torch.zeros(n, L, dtype=torch.int32)
+    for j in range(L):
+        spread = 1 + min(W - 1, max(0, j - (pos - 12)))
+        anc[:, j] = (torch.arange(n) // W) * W + torch.randint(0, spread, (n,), generator=g)
+    anc = anc.to(dev)
+    ctx = torch.empty(2, n, D, device=dev)
+    alg = n * 3 * D * 4 + 2 * n * D * 4 * 2
+    timeit(f"dec_self_attn n{n} H8 pos{pos}", lambda: call("espb_dec_self_attn_f32", ptr(qkv), ptr(kc), ptr(vc), ptr(anc), L, n, D, H, pos, None, L, ptr(ctx), n * D), alg)

@@ -13,7 +13,9 @@ for r in csv.DictReader(lines):
         unit = r.get("Metric Unit", "ns")
         ns = v * {"ns": 1, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6, "nsecond": 1, "s": 1e9, "second": 1e9}.get(unit, 1)
         name = re.sub(r"\(.*", "", r["Kernel Name"])
-        name = re.sub(r"^void |\(anonymous namespace\)::", "", name)
+        name = re.sub(r"^void |\(anonymous namespace\)::|<unnamed>::", "", name)
+        if "gemm" in name:   # GEMMs: one line per tile configuration and grid (decode-step vs encoder problems)
+            name += " grid" + r.get("Grid Size", "").replace(" ", "")
         rows.append((name, ns))
 tot = sum(ns for _, ns in rows)
 agg = collections.defaultdict(lambda: [0, 0.0])
