@@ -261,6 +261,37 @@ def run_b200(args, rank, local_rank, world):
         for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
             print(f"[breakdown] {100 * ms / tot:6.2f}%  {ms:9.3f} ms  {c:5d}x  avg {1e3 * ms / c:9.1f} us  {k}", file=sys.stderr)
         return
+    if args.trace:   # CUPTI activity trace (torch.profiler) of one step: in-situ kernel durations inside the replayed CUDA graphs
+        import collections
+        import re as _re
+
+        from torch.profiler import ProfilerActivity, profile
+
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_resident(speech_dev)
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start]
+        evs.sort(key=lambda e: e.time_range.start)
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for e in evs:
+            name = _re.sub(r"^void |\(anonymous namespace\)::|<unnamed>::", "", e.name)
+            name = _re.sub(r"\(.*", "", name)
+            agg[name][0] += 1
+            agg[name][1] += (e.time_range.end - e.time_range.start)
+        t_first, t_last = evs[0].time_range.start, max(e.time_range.end for e in evs)
+        busy, cur_end = 0.0, t_first           # union of kernel intervals (streams overlap)
+        for e in evs:
+            st, en = max(e.time_range.start, cur_end), e.time_range.end
+            if en > st:
+                busy += en - st
+                cur_end = en
+        tot = sum(v[1] for v in agg.values())
+        print(f"[trace] {args.workload}: {len(evs)} device activities, span {(t_last - t_first) / 1e3:.2f} ms, device busy (union) {busy / 1e3:.2f} ms, "
+              f"sum of durations {tot / 1e3:.2f} ms", file=sys.stderr)
+        for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:50]:
+            print(f"[trace] {100 * us / tot:6.2f}%  {us / 1e3:9.3f} ms  {c:5d}x  avg {us / c:9.1f} us  {k[:120]}", file=sys.stderr)
+        return
     if args.profile_one_step:   # for ncu --profile-from-start off: exactly one resident step inside the profiler range
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -364,6 +395,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="conformer_large_joint_64x30s", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--trace", action="store_true", help="CUPTI activity trace of one step (kernel durations inside the CUDA graphs) -> stderr")
     ap.add_argument("--breakdown", action="store_true", help="time every launch of one step with CUDA events and print a per-kernel table")
     ap.add_argument("--profile-one-step", action="store_true", help="warm up, then run one step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()

@@ -254,38 +254,54 @@ class BatchBeamSearch(torch.nn.Module):
         return self._streams[key]
 
     def _collect(self, U, W, steps, maxlen, bp_parent, bp_token, e_count, e_step, e_slot, e_score, e_dec, e_ctc):
-        """Host post-processing: rebuild token sequences from back-pointers and sort (beam_search.py:452-459)."""
+        """Host post-processing: rebuild token sequences from back-pointers and sort (beam_search.py:452-459).
+        The back-pointer walk is vectorised over all ended hypotheses (one numpy gather per position)."""
+        import numpy as np
+
         bpp, bpt = bp_parent[:steps].cpu().numpy(), bp_token[:steps].cpu().numpy()
-        cnt = e_count.cpu().numpy()
+        cnt = e_count.cpu().numpy().astype(np.int64)
         es, el = e_step.cpu().numpy(), e_slot.cpu().numpy()
         sc, sd, sct = e_score.cpu().numpy(), e_dec.cpu().numpy(), e_ctc.cpu().numpy()
-        results = []
+        cap_e = es.shape[1]
+        sel = np.arange(cap_e)[None, :] < cnt[:, None]                    # [U][cap_e] valid ended entries, utterance-major order
+        uu, ee = np.nonzero(sel)
+        nh = uu.shape[0]
+        step_h, slot_h = es[uu, ee].astype(np.int64), el[uu, ee].astype(np.int64)
+        mlen = np.asarray([int(m) for m in maxlen], dtype=np.int64)[uu] if nh else np.zeros(0, np.int64)
+        L = int(step_h.max()) + 1 if nh else 0
+        # yseq = [sos] + tokens(0..step) (+ eos if the hypothesis was cut at maxlen, batch_beam_search.py:392-407)
+        seq = np.full((nh, L + 2), self.eos, dtype=np.int64)
+        if nh:
+            seq[:, 0] = self.sos
+            s = slot_h.copy()
+            for j in range(L - 1, -1, -1):
+                live = step_h >= j
+                sj = s[live]
+                seq[live, j + 1] = bpt[j, sj]
+                s[live] = bpp[j, sj]
+        at_max = step_h == mlen - 1
+        length = step_h + 2 + at_max                                      # sos + (step+1) tokens (+ appended eos)
+        seq_t = torch.from_numpy(seq)
+        score_h, dec_h, ctc_h = sc[uu, ee], sd[uu, ee], sct[uu, ee]
+        key = score_h / (length - 1) if self.normalize_length else score_h
+        results = [[] for _ in range(U)]
+        start = np.concatenate([[0], np.cumsum(cnt)])
+        has_dec, has_ctc, has_pen = self.decoder is not None, self.ctc is not None, self.penalty != 0
         for u in range(U):
-            hyps = []
-            for e in range(int(cnt[u])):
-                step, slot = int(es[u, e]), int(el[u, e])
-                toks = []
-                s = slot
-                for j in range(step, -1, -1):
-                    toks.append(int(bpt[j, s]))
-                    s = int(bpp[j, s])
-                toks.reverse()
-                yseq = [self.sos] + toks
-                if step == int(maxlen[u]) - 1:
-                    yseq.append(self.eos)  # "adding <eos> in the last position in the loop" (batch_beam_search.py:392-407)
+            lo, hi = int(start[u]), int(start[u + 1])
+            if hi == lo:
+                continue
+            order = lo + np.argsort(-key[lo:hi], kind="stable")         # descending, ties keep ended order (list.sort is stable)
+            hyps = results[u]
+            for i in order.tolist():
                 scores = {}
-                if self.decoder is not None:
-                    scores["decoder"] = float(sd[u, e])
-                if self.ctc is not None:
-                    scores["ctc"] = float(sct[u, e])
-                if self.penalty != 0:
-                    scores["length_bonus"] = float(step + 1)
-                hyps.append(Hypothesis(yseq=torch.tensor(yseq, dtype=torch.int64), score=float(sc[u, e]), scores=scores))
-            if self.normalize_length:
-                hyps.sort(key=lambda h: h.score / (len(h.yseq) - 1), reverse=True)
-            else:
-                hyps.sort(key=lambda h: h.score, reverse=True)
-            results.append(hyps)
+                if has_dec:
+                    scores["decoder"] = float(dec_h[i])
+                if has_ctc:
+                    scores["ctc"] = float(ctc_h[i])
+                if has_pen:
+                    scores["length_bonus"] = float(step_h[i] + 1)
+                hyps.append(Hypothesis(yseq=seq_t[i, : int(length[i])], score=float(score_h[i]), scores=scores))
         return results
 
     def forward(self, x, maxlenratio=0.0, minlenratio=0.0):
