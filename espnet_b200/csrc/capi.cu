@@ -6,7 +6,7 @@
 #include "gemm.h"
 
 #ifndef ESPB_PDL_DEFAULT
-#define ESPB_PDL_DEFAULT 0
+#define ESPB_PDL_DEFAULT 1
 #endif
 
 static thread_local char g_err[512] = "";

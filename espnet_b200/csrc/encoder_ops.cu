@@ -61,6 +61,62 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// 128-bit variant (D % 4 == 0, 16-byte aligned rows): x, gamma and beta are all requested before the first reduction, so one
+// memory round trip covers them; small problems (decode step: a few hundred rows) use 2 rows per block to spread over all SMs.
+template <int NV4>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, long long rows, int D, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, float* __restrict__ out_plain,
+                                                            float* __restrict__ out_split, long long split_plane) {
+  espb::pdl_trigger();
+  espb::pdl_wait();
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * D;
+  float4 v[NV4], g[NV4], b[NV4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = (lane + i * 32) * 4;
+    if (c < D) {
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      g[i] = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      b[i] = __ldg(reinterpret_cast<const float4*>(beta + c));
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f); g[i] = v[i]; b[i] = v[i];
+    }
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = espb::warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = (lane + i * 32) * 4;
+    if (c < D) {
+      const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(espb::warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = (lane + i * 32) * 4;
+    if (c < D) {
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g[i].x + b[i].x; y.y = (v[i].y - mean) * rstd * g[i].y + b[i].y;
+      y.z = (v[i].z - mean) * rstd * g[i].z + b[i].z; y.w = (v[i].w - mean) * rstd * g[i].w + b[i].w;
+      if (out_plain) *reinterpret_cast<float4*>(out_plain + row * D + c) = y;
+      if (out_split) {
+        float4 hi, lo;
+        hi.x = espb::tf32_hi(y.x); hi.y = espb::tf32_hi(y.y); hi.z = espb::tf32_hi(y.z); hi.w = espb::tf32_hi(y.w);
+        lo.x = espb::tf32_lo(y.x, hi.x); lo.y = espb::tf32_lo(y.y, hi.y); lo.z = espb::tf32_lo(y.z, hi.z); lo.w = espb::tf32_lo(y.w, hi.w);
+        *reinterpret_cast<float4*>(out_split + row * D + c) = hi;
+        *reinterpret_cast<float4*>(out_split + split_plane + row * D + c) = lo;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- fp32 -> hi/lo planes (weights, pos-emb)
 __global__ void split_kernel(const float* __restrict__ x, long long n, float* __restrict__ out, long long plane) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -304,6 +360,19 @@ int espb_layernorm_f32(const float* x, long long rows, int D, const float* gamma
                        float* out_split, long long split_plane, cudaStream_t stream) {
   if (D > 2048 || D <= 0) { espb_set_error("layernorm: D must be in (0, 2048]"); return ESPB_ERR_ARG; }
   if (rows <= 0) return ESPB_OK;
+  {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                         reinterpret_cast<uintptr_t>(out_plain) | reinterpret_cast<uintptr_t>(out_split);
+    if ((D & 3) == 0 && D <= 1024 && (al & 15) == 0 && (split_plane & 3) == 0 && !getenv("ESPB_LN_SCALAR")) {
+      const int rpb = rows <= 4096 ? 2 : 8;   // rows (warps) per block
+      const dim3 g((unsigned)((rows + rpb - 1) / rpb)), blk(32 * rpb);
+      if (D <= 256) espb::launch_pdl(layernorm_vec_kernel<2>, g, blk, 0, stream, x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+      else if (D <= 512) espb::launch_pdl(layernorm_vec_kernel<4>, g, blk, 0, stream, x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+      else espb::launch_pdl(layernorm_vec_kernel<8>, g, blk, 0, stream, x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
+      ESPB_CHECK_LAUNCH();
+      return ESPB_OK;
+    }
+  }
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (D <= 256) espb::launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), 0, stream, x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);
   else if (D <= 512) espb::launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(256), 0, stream, x, rows, D, gamma, beta, eps, out_plain, out_split, split_plane);

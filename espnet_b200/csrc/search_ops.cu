@@ -579,19 +579,19 @@ __device__ __forceinline__ float ctc_phi(const float4* __restrict__ rp, int t, b
 // log_psi of extending the prefix of a slot by token c (ctc_prefix_score.py:166-189).  It depends only on the PREVIOUS state:
 //   log_psi = logsumexp( {log_phi[t-1] + x[t,c]}_{t=start..T-1}, r[start-1,0] ),   r[start-1,0] = x[0,c] if the prefix is empty else logzero
 // so it is a reduction over t: one warp per (slot, candidate), lanes stride t.  Must be called by a full warp.
-__device__ __forceinline__ float ctc_log_psi_warp(const float* __restrict__ x, int V, int T, int blank, int eos, const float4* __restrict__ rp, int c,
-                                                  int last, int out_len, int lane) {
+__device__ __forceinline__ float ctc_log_psi_warp(const float* __restrict__ x, long long st_t, long long st_c, int T, int blank, int eos,
+                                                  const float4* __restrict__ rp, int c, int last, int out_len, int lane) {
   if (c == eos) return __ldg(rp + (T - 1)).z;                             // (:184-185) r_sum[T-1]
   if (c == blank) return LOGZERO;                                          // (:187-189)
   const int start = max(out_len, 1);
   const bool same = (c == last);
   float m = -INFINITY, ssum = 0.f;   // per-lane streaming log-sum-exp, merged across the warp at the end
   for (int t = start + lane; t < T; t += 32) {
-    const float e = ctc_phi(rp, t - 1, same) + __ldg(x + (long long)t * V + c);
+    const float e = ctc_phi(rp, t - 1, same) + __ldg(x + t * st_t + c * st_c);
     if (e > m) { ssum = ssum * expf(m - e) + 1.f; m = e; } else { ssum += expf(e - m); }
   }
   if (lane == 0) {   // the r[start-1,0] term
-    const float r0 = (out_len == 0) ? x[c] : LOGZERO;
+    const float r0 = (out_len == 0) ? x[c * st_c] : LOGZERO;
     if (r0 > m) { ssum = ssum * expf(m - r0) + 1.f; m = r0; } else { ssum += expf(r0 - m); }
   }
 #pragma unroll
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(256) ctc_score_cands_kernel(const float* __res
                                                               int eos, int W, int n, const float* __restrict__ r_prev, const float* __restrict__ s_prev,
                                                               const int* __restrict__ last_tok, int out_len, const int* __restrict__ step_ptr,
                                                               const int* __restrict__ cand, int P, float* __restrict__ part,
-                                                              float* __restrict__ psi, int* __restrict__ valid) {
+                                                              float* __restrict__ psi, int* __restrict__ valid, int token_major) {
   if (step_ptr) out_len += *step_ptr;
   const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -620,8 +620,9 @@ __global__ void __launch_bounds__(256) ctc_score_cands_kernel(const float* __res
   const int c = (j < P) ? cand[(long long)s * P + j] : eos;
   int ok = 1;
   if (j == P) for (int q = 0; q < P; ++q) if (cand[(long long)s * P + q] == eos) ok = 0;
-  const float v = ctc_log_psi_warp(logp + (long long)u * Tmax * V, V, lens[u], blank, eos, reinterpret_cast<const float4*>(r_prev) + (long long)s * Tmax, c, last_tok[s],
-                                   out_len, lane);
+  // token_major: logp is [u][v][t] (a candidate's column is contiguous in t -> coalesced); else [u][t][v]
+  const float v = ctc_log_psi_warp(logp + (long long)u * Tmax * V, token_major ? 1 : V, token_major ? Tmax : 1, lens[u], blank, eos,
+                                   reinterpret_cast<const float4*>(r_prev) + (long long)s * Tmax, c, last_tok[s], out_len, lane);
   if (lane == 0) { psi[idx] = v; part[idx] = v - s_prev[s]; valid[idx] = ok; }
 }
 
@@ -791,7 +792,7 @@ __global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restric
                                                           int W, int n, const float* __restrict__ r_prev, const int* __restrict__ parent,
                                                           const int* __restrict__ par_last_tok, const int* __restrict__ new_tok,
                                                           const int* __restrict__ new_active, int out_len, const int* __restrict__ step_ptr,
-                                                          float* __restrict__ r_new, float* __restrict__ s_new) {
+                                                          float* __restrict__ r_new, float* __restrict__ s_new, int token_major) {
   if (step_ptr) out_len += *step_ptr;
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -807,17 +808,18 @@ __global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restric
   }
   const int p = parent[s], T = lens[u];
   const float* x = logp + (long long)u * Tmax * V;
+  const long long st_t = token_major ? 1 : V, st_c = token_major ? Tmax : 1;
   const float4* rp = reinterpret_cast<const float4*>(r_prev) + (long long)p * Tmax;
   const int last = par_last_tok[p];
   const bool same = (c == last);
   const int start = max(out_len, 1);
-  float rn = (out_len == 0) ? x[c] : LOGZERO, rb = LOGZERO;   // r[start-1]
+  float rn = (out_len == 0) ? x[c * st_c] : LOGZERO, rb = LOGZERO;   // r[start-1]
   for (int t = lane; t < start - 1; t += 32) ro[t] = Z4;
   if (lane == 0) ro[start - 1] = make_float4(rn, rb, logaddexp(rn, rb), 0.f);
   for (int t0 = start; t0 < T; t0 += 32) {
     const int t = t0 + lane;
     float phi = LOGZERO, xc = 0.f, xb = 0.f;
-    if (t < T) { phi = ctc_phi(rp, t - 1, same); xc = x[(long long)t * V + c]; xb = x[(long long)t * V + blank]; }
+    if (t < T) { phi = ctc_phi(rp, t - 1, same); xc = x[t * st_t + c * st_c]; xb = x[t * st_t + blank * st_c]; }
     float my_n = LOGZERO, my_b = LOGZERO;
     const int cnt = min(32, T - t0);
     for (int i = 0; i < cnt; ++i) {
@@ -830,8 +832,24 @@ __global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restric
     if (t < T) ro[t] = make_float4(my_n, my_b, logaddexp(my_n, my_b), 0.f);
   }
   for (int t = T + lane; t < Tmax; t += 32) ro[t] = Z4;
-  const float psi = ctc_log_psi_warp(x, V, T, blank, eos, rp, c, last, out_len, lane);
+  const float psi = ctc_log_psi_warp(x, st_t, st_c, T, blank, eos, rp, c, last, out_len, lane);
   if (lane == 0) s_new[s] = psi;
+}
+
+// CTC posteriors [u][t][v] -> [u][v][t]: the per-step candidate scoring / state advance read whole token columns.
+__global__ void __launch_bounds__(256) transpose_tv_kernel(const float* __restrict__ x, int Tmax, int V, float* __restrict__ xt) {
+  __shared__ float tile[32][33];
+  const long long base = (long long)blockIdx.z * Tmax * V;
+  const int v0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, v = v0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < Tmax && v < V) ? x[base + (long long)t * V + v] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int v = v0 + i, t = t0 + threadIdx.x;
+    if (v < V && t < Tmax) xt[base + (long long)v * Tmax + t] = tile[threadIdx.x][i];
+  }
 }
 
 __global__ void step_inc_kernel(int* step) { *step += 1; }
@@ -949,10 +967,10 @@ int espb_ctc_init_state_f32(const float* logp, int U, int Tmax, int V, const int
 
 int espb_ctc_score_cands_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
                              const float* s_prev, const int* last_tok, int out_len, const int* step_ptr, const int* cand, int P, float* part,
-                             float* psi, int* valid, cudaStream_t stream) {
+                             float* psi, int* valid, int token_major, cudaStream_t stream) {
   const int n = U * W, tot = n * (P + 1);
   ctc_score_cands_kernel<<<(tot + 7) / 8, 256, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, s_prev, last_tok, out_len, step_ptr, cand,
-                                                              P, part, psi, valid);
+                                                              P, part, psi, valid, token_major);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
@@ -998,10 +1016,17 @@ int espb_anc_update_i32(const int* anc, int* n_anc, int anc_ld, const int* paren
 
 int espb_ctc_advance_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
                          const int* parent, const int* par_last_tok, const int* new_tok, const int* new_active, int out_len, const int* step_ptr,
-                         float* r_new, float* s_new, cudaStream_t stream) {
+                         float* r_new, float* s_new, int token_major, cudaStream_t stream) {
   const int n = U * W;
   ctc_advance_kernel<<<(n + 3) / 4, 128, 0, stream>>>(logp, Tmax, V, lens, blank, eos, W, n, r_prev, parent, par_last_tok, new_tok, new_active,
-                                                       out_len, step_ptr, r_new, s_new);
+                                                       out_len, step_ptr, r_new, s_new, token_major);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_transpose_tv_f32(const float* x, int U, int Tmax, int V, float* xt, cudaStream_t stream) {
+  dim3 grid((V + 31) / 32, (Tmax + 31) / 32, U), block(32, 8);
+  transpose_tv_kernel<<<grid, block, 0, stream>>>(x, Tmax, V, xt);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

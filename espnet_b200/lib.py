@@ -56,12 +56,13 @@ _SIGS = {
     "espb_dec_src_attn_f32": [P, P, P, I, I, P, I, I, I, P, L, P],
     "espb_rows_topk_f32": [P, L, L, I, F, I, P, P, P],
     "espb_ctc_init_state_f32": [P, I, I, I, P, I, I, P, P, P],
-    "espb_ctc_score_cands_f32": [P, I, I, I, P, I, I, I, P, P, P, I, P, P, I, P, P, P, P],
+    "espb_ctc_score_cands_f32": [P, I, I, I, P, I, I, I, P, P, P, I, P, P, I, P, P, P, I, P],
     "espb_ctc_score_dense_f32": [P, I, I, I, P, I, I, I, P, P, P, I, P, P],
     "espb_beam_select": [P] * 18 + [I] + [P, P, P] + [I, I, I, I, I, P, P, P, I, F, F, F, I, P, P, P, P, P, I, I, P],
     "espb_anc_update_i32": [P, P, I, P, I, P, I, P],
     "espb_step_inc_i32": [P, P],
-    "espb_ctc_advance_f32": [P, I, I, I, P, I, I, I, P, P, P, P, P, I, P, P, P, P],
+    "espb_ctc_advance_f32": [P, I, I, I, P, I, I, I, P, P, P, P, P, I, P, P, P, I, P],
+    "espb_transpose_tv_f32": [P, I, I, I, P, P],
     "espb_count_active_i32": [P, I, P, P],
 }
 

@@ -90,6 +90,7 @@ class BatchBeamSearch(torch.nn.Module):
             st["s_prev"] = [f32(n), f32(n)]
             if mode == 1:
                 st["part"], st["psi"], st["valid"] = f32(n, PC), f32(n, PC), i32(n, PC)
+                st["logp_ctc_t"] = f32(U * V, Tmax)
             else:
                 st["part"] = f32(n, V)
         cache[key] = st
@@ -142,6 +143,11 @@ class BatchBeamSearch(torch.nn.Module):
             r, s_prev = st["r"], st["s_prev"]
             call("espb_ctc_init_state_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, W, ptr(r[0]), ptr(s_prev[0]))
             _count()
+            logp_tok, tok_major = logp_ctc, 0
+            if mode == 1:   # token-major copy [U][V][Tmax]: the per-step candidate columns become contiguous reads
+                logp_tok, tok_major = st["logp_ctc_t"], 1
+                call("espb_transpose_tv_f32", ptr(logp_ctc), U, Tmax, V, ptr(logp_tok))
+                _count()
         end_detect = 1 if maxlenratio == 0.0 else 0
         side = self._side_stream(dev) if (use_ctc and use_dec) else None
 
@@ -155,8 +161,8 @@ class BatchBeamSearch(torch.nn.Module):
                 # CTC forward variables of the hypotheses chosen in the previous step (scorers/ctc.py:40-63): only the scoring below needs
                 # them, so the T-step recursion runs on a side stream concurrently with the decoder pass
                 def advance():
-                    call("espb_ctc_advance_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[nxt]), ptr(parent),
-                         ptr(last_tok[nxt]), ptr(last_tok[cur]), ptr(active[cur]), iv - 1, ptr(sp), ptr(r[cur]), ptr(s_prev[cur]))
+                    call("espb_ctc_advance_f32", ptr(logp_tok), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[nxt]), ptr(parent),
+                         ptr(last_tok[nxt]), ptr(last_tok[cur]), ptr(active[cur]), iv - 1, ptr(sp), ptr(r[cur]), ptr(s_prev[cur]), tok_major)
                     _count()
                 if side is not None:
                     ev = torch.cuda.Event()
@@ -172,8 +178,8 @@ class BatchBeamSearch(torch.nn.Module):
                 main.wait_stream(side)
             if mode == 1:
                 ops.rows_topk(logp_dec, self.w_dec, P, st["cand_ids"], st["cand_val"])
-                call("espb_ctc_score_cands_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
-                     ptr(last_tok[cur]), iv, ptr(sp), ptr(st["cand_ids"]), P, ptr(st["part"]), ptr(st["psi"]), ptr(st["valid"]))
+                call("espb_ctc_score_cands_f32", ptr(logp_tok), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
+                     ptr(last_tok[cur]), iv, ptr(sp), ptr(st["cand_ids"]), P, ptr(st["part"]), ptr(st["psi"]), ptr(st["valid"]), tok_major)
                 _count()
             elif mode == 0:
                 ops.rows_topk(logp_dec, self.w_dec, P, st["cand_ids"], st["cand_val"])

@@ -120,12 +120,15 @@ int espb_ctc_init_state_f32(const float* logp, int U, int Tmax, int V, const int
                             cudaStream_t stream);
 int espb_ctc_score_cands_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
                              const float* s_prev, const int* last_tok, int out_len, const int* step_ptr, const int* cand, int P, float* part,
-                             float* psi, int* valid, cudaStream_t stream);
+                             float* psi, int* valid, int token_major, cudaStream_t stream);
 int espb_ctc_score_dense_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
                              const float* s_prev, const int* last_tok, int out_len, float* part, cudaStream_t stream);
 int espb_ctc_advance_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
                          const int* parent, const int* par_last_tok, const int* new_tok, const int* new_active, int out_len, const int* step_ptr,
-                         float* r_new, float* s_new, cudaStream_t stream);
+                         float* r_new, float* s_new, int token_major, cudaStream_t stream);
+/* logp [U][Tmax][V] -> xt [U][V][Tmax]; espb_ctc_score_cands_f32 / espb_ctc_advance_f32 with token_major = 1 read this layout (each
+ * candidate's posterior column is then one contiguous, coalesced read instead of a stride-V gather). */
+int espb_transpose_tv_f32(const float* x, int U, int Tmax, int V, float* xt, cudaStream_t stream);
 /* Weighted sum + beam top-k over (hyps x candidates) per utterance + post_process (eos / maxlen / minlen / end_detect).
  * mode 0 decoder only, 1 joint (pre-beam candidates + eos), 2 CTC only (dense). */
 int espb_beam_select(const float* score, const float* sc_dec, const float* sc_ctc, const int* active, float* n_score, float* n_sc_dec,

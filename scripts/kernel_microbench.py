@@ -75,3 +75,26 @@ if which in ("selfattn", "all"):
     ctx = torch.empty(2, n, D, device=dev)
     alg = n * 3 * D * 4 + 2 * n * D * 4 * 2
     timeit(f"dec_self_attn n{n} H8 pos{pos}", lambda: call("espb_dec_self_attn_f32", ptr(qkv), ptr(kc), ptr(vc), ptr(anc), L, n, D, H, pos, None, L, ptr(ctx), n * D), alg)
+
+if which in ("ln", "all"):
+    rows, D = 640, 512
+    x = torch.randn(rows, D, device=dev)
+    g, b = torch.randn(D, device=dev), torch.randn(D, device=dev)
+    out = torch.empty(2, rows, D, device=dev)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        fn = lambda: call("espb_layernorm_f32", ptr(x), rows, D, ptr(g), ptr(b), 1e-12, None, ptr(out), rows * D)  # noqa: E731
+        fn()
+        s.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            for _ in range(100):
+                fn()
+        gr.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(5):
+            gr.replay()
+        e1.record(s)
+        s.synchronize()
+    print(f"[kernel_microbench] layernorm {rows}x{D} in-graph back-to-back: {e0.elapsed_time(e1) * 1e3 / 500:6.2f} us/launch")
