@@ -105,7 +105,10 @@ class TransformerDecoder(torch.nn.Module):
         self._packed = pk
         return pk
 
+    ws_tag = 0   # workspace set in use: the search runs independent utterance groups on separate streams, each with its own buffers
+
     def _buf(self, name, shape, dtype=torch.float32, zero=False):
+        name = (self.ws_tag, name)
         key = (name, tuple(shape), dtype)
         t = self._ws.get(key)
         if t is None:

@@ -62,15 +62,15 @@ class BatchBeamSearch(torch.nn.Module):
             raise NotImplementedError("beam_size > 32 (the per-utterance beam selection runs in one warp)")
 
     # ---------------------------------------------------------------- search state (cached per shape so that CUDA graphs can be reused)
-    def _state(self, dev, U, Tmax, W, V, cap, mode, P):
-        key = (str(dev), U, Tmax, W, V, cap, mode, P)
+    def _state(self, dev, U, Tmax, W, V, cap, mode, P, g=0):
+        key = (str(dev), U, Tmax, W, V, cap, mode, P, g)
         cache = getattr(self, "_state_cache", None)
         if cache is None:
             cache = self._state_cache = {}
         st = cache.get(key)
         if st is not None:
             return st
-        if len(cache) >= 4:
+        if len(cache) >= 8:
             cache.clear()
         n, PC = U * W, (P + 1 if mode == 1 else P)
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)  # noqa: E731
@@ -97,151 +97,81 @@ class BatchBeamSearch(torch.nn.Module):
         return st
 
     use_cuda_graphs = True   # replay one captured graph per step parity once the buffers are warm (steps >= 4)
+    # Utterances are independent, and one decoding step is a chain of ~80 small dependent kernels that each fill only part of the GPU:
+    # batches of >= group_min_utts utterances are searched as n_groups independent groups on their own streams (own state, decoder
+    # workspace and CUDA graphs), stepped in lock-step from the host so that the groups' kernel chains overlap on the device.
+    group_min_utts = 16
+    n_groups = 2
+
+    def _group_bounds(self, U):
+        import os
+
+        G = int(os.environ.get("ESPB_SEARCH_GROUPS", self.n_groups))
+        if G <= 1 or U < self.group_min_utts or U < 2 * G:
+            return [(0, U)]
+        base, rem = divmod(U, G)
+        bounds, u0 = [], 0
+        for g in range(G):
+            u1 = u0 + base + (1 if g < rem else 0)
+            bounds.append((u0, u1))
+            u0 = u1
+        return bounds
 
     @torch.no_grad()
     def forward_batch(self, enc, enc_lens, enc_split=None, maxlenratio=0.0, minlenratio=0.0, check_every=8):
         """enc (U, Tmax, D) CUDA, enc_lens (U,) -> list (per utterance) of n-best Hypothesis lists, sorted."""
-        from . import lib as _lib
-
-        dev = enc.device
         U, Tmax, D = enc.shape
-        W, V = self.beam_size, self.n_vocab
-        n = U * W
-        lens_cpu = enc_lens.detach().cpu().to(torch.int64)
-        if maxlenratio == 0:
-            maxlen = lens_cpu.clone()
-        elif maxlenratio < 0:
-            maxlen = torch.full_like(lens_cpu, -int(maxlenratio))
-        else:
-            maxlen = torch.clamp((maxlenratio * lens_cpu.double()).long(), min=1)
-        minlen = torch.full_like(lens_cpu, -int(minlenratio)) if minlenratio < 0 else (minlenratio * lens_cpu.double()).long()
-        cap = int(maxlen.max())
-        if enc_split is None:
-            enc_split = ops.split_from(enc.contiguous().view(U * Tmax, D))
-        use_dec, use_ctc = self.decoder is not None, self.ctc is not None
-        mode = 1 if (use_dec and use_ctc) else (0 if use_dec else 2)
-        P = self.pre_beam_size if mode == 1 else W
-        st = self._state(dev, U, Tmax, W, V, cap, mode, P)
+        bounds = self._group_bounds(U)
+        if len(bounds) == 1:
+            run = _SearchRun(self, 0, None, enc, enc_lens, enc_split, maxlenratio, minlenratio)
+            self._drive([run], check_every)
+            return run.collect()
+        main = torch.cuda.current_stream()
+        lens_cpu = enc_lens.detach().cpu()
+        runs = []
+        for g, (u0, u1) in enumerate(bounds):
+            sg = self._group_stream(enc.device, g)
+            sg.wait_stream(main)
+            with torch.cuda.stream(sg):
+                es_g = None
+                if enc_split is not None:   # hi/lo planes of this group's rows as one contiguous split tensor
+                    es_g = enc_split.view(2, U * Tmax, D)[:, u0 * Tmax:u1 * Tmax].contiguous()
+                runs.append(_SearchRun(self, g, sg, enc[u0:u1], lens_cpu[u0:u1], es_g, maxlenratio, minlenratio))
+        self._drive(runs, check_every)
+        out = []
+        for r in runs:
+            with torch.cuda.stream(r.stream):
+                out.extend(r.collect())
+            main.wait_stream(r.stream)
+        return out
 
-        # ---- (re)initialise the state in place: one hypothesis [sos] per utterance (batch_beam_search.py:124-153)
-        for k in ("score", "sc_dec", "sc_ctc", "active"):
-            st[k][0].zero_(); st[k][1].zero_()
-        st["active"][0].view(U, W)[:, 0] = 1
-        st["last_tok"][0].fill_(self.sos); st["last_tok"][1].fill_(self.sos)
-        st["bp_parent"].fill_(-1); st["bp_token"].fill_(self.eos)
-        st["e_count"].zero_(); st["done"].zero_()
-        st["best_at"].fill_(float("-inf")); st["best_all"].fill_(float("-inf"))
-        st["lens32"].copy_(lens_cpu.to(torch.int32)); st["maxlen"].copy_(maxlen.to(torch.int32)); st["minlen"].copy_(minlen.to(torch.int32))
-        st["step"].zero_()
-        lens32, step_dev = st["lens32"], st["step"]
-        score, sc_dec, sc_ctc, active, last_tok = st["score"], st["sc_dec"], st["sc_ctc"], st["active"], st["last_tok"]
-        parent, anc = st["parent"], st["anc"]
-        dst = self.decoder.init_memory(enc_split, U, Tmax, lens32, n, cap) if use_dec else None
-        logp_ctc = r = s_prev = None
-        if use_ctc:
-            logp_ctc = self.ctc.log_softmax(enc, enc_split, out=st["logp_ctc"])   # (U, Tmax, V), scorers/ctc.py:96-99
-            r, s_prev = st["r"], st["s_prev"]
-            call("espb_ctc_init_state_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, W, ptr(r[0]), ptr(s_prev[0]))
-            _count()
-            logp_tok, tok_major = logp_ctc, 0
-            if mode == 1:   # token-major copy [U][V][Tmax]: the per-step candidate columns become contiguous reads
-                logp_tok, tok_major = st["logp_ctc_t"], 1
-                call("espb_transpose_tv_f32", ptr(logp_ctc), U, Tmax, V, ptr(logp_tok))
-                _count()
-        end_detect = 1 if maxlenratio == 0.0 else 0
-        side = self._side_stream(dev) if (use_ctc and use_dec) else None
+    def _drive(self, runs, check_every):
+        """Host loop: step i of every unfinished group is enqueued before any group is polled for termination."""
+        import contextlib
 
-        def step_body(i, cur, sp):
-            """One search step. `sp` is None (host step index i) or the device step counter (graph mode: i is ignored)."""
-            nxt = cur ^ 1
-            iv = 0 if sp is not None else i
-            main = torch.cuda.current_stream()
-            forked = False
-            if use_ctc and (sp is not None or i >= 1):
-                # CTC forward variables of the hypotheses chosen in the previous step (scorers/ctc.py:40-63): only the scoring below needs
-                # them, so the T-step recursion runs on a side stream concurrently with the decoder pass
-                def advance():
-                    call("espb_ctc_advance_f32", ptr(logp_tok), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[nxt]), ptr(parent),
-                         ptr(last_tok[nxt]), ptr(last_tok[cur]), ptr(active[cur]), iv - 1, ptr(sp), ptr(r[cur]), ptr(s_prev[cur]), tok_major)
-                    _count()
-                if side is not None:
-                    ev = torch.cuda.Event()
-                    ev.record(main)
-                    with torch.cuda.stream(side):
-                        side.wait_event(ev)
-                        advance()
-                    forked = True
-                else:
-                    advance()
-            logp_dec = self.decoder.step(dst, iv, last_tok[cur], anc[cur], W, sp) if use_dec else None
-            if forked:
-                main.wait_stream(side)
-            if mode == 1:
-                ops.rows_topk(logp_dec, self.w_dec, P, st["cand_ids"], st["cand_val"])
-                call("espb_ctc_score_cands_f32", ptr(logp_tok), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
-                     ptr(last_tok[cur]), iv, ptr(sp), ptr(st["cand_ids"]), P, ptr(st["part"]), ptr(st["psi"]), ptr(st["valid"]), tok_major)
-                _count()
-            elif mode == 0:
-                ops.rows_topk(logp_dec, self.w_dec, P, st["cand_ids"], st["cand_val"])
-            else:
-                call("espb_ctc_score_dense_f32", ptr(logp_ctc), U, Tmax, V, ptr(lens32), 0, self.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
-                     ptr(last_tok[cur]), i, ptr(st["part"]))
-                _count()
-                ops.rows_topk(st["part"], self.w_ctc, P, st["cand_ids"], st["cand_val"])
-            call("espb_beam_select", ptr(score[cur]), ptr(sc_dec[cur]), ptr(sc_ctc[cur]), ptr(active[cur]), ptr(score[nxt]),
-                 ptr(sc_dec[nxt]), ptr(sc_ctc[nxt]), ptr(active[nxt]), ptr(last_tok[nxt]), ptr(parent), ptr(st["bp_parent"]),
-                 ptr(st["bp_token"]), ptr(st["e_count"]), ptr(st["e_step"]), ptr(st["e_slot"]), ptr(st["e_score"]), ptr(st["e_dec"]),
-                 ptr(st["e_ctc"]), st["ended_cap"], ptr(st["best_at"]), ptr(st["best_all"]), ptr(st["done"]), U, W, P, V, iv, ptr(sp),
-                 ptr(st["maxlen"]), ptr(st["minlen"]), self.eos, self.w_dec, self.w_ctc, self.penalty, mode, ptr(st["cand_ids"]),
-                 ptr(st["cand_val"]), ptr(logp_dec), ptr(st.get("part")), ptr(st.get("valid")), end_detect, cap)
-            _count()
-            if use_dec:
-                call("espb_anc_update_i32", ptr(anc[cur]), ptr(anc[nxt]), cap + 1, ptr(parent), iv, ptr(sp), n)
-                _count()
-            if sp is not None:
-                call("espb_step_inc_i32", ptr(sp))
-                _count()
+        ctx = lambda r: torch.cuda.stream(r.stream) if r.stream is not None else contextlib.nullcontext()  # noqa: E731
+        for i in range(max(r.cap for r in runs)):
+            live = [r for r in runs if not r.finished and i < r.cap]
+            if not live:
+                break
+            for r in live:
+                with ctx(r):
+                    r.step(i)
+            for r in live:
+                if (i + 1) % check_every == 0 or r.end_detect:
+                    with ctx(r):
+                        r.poll(i)
+        for r in runs:
+            with ctx(r):
+                r.join()
 
-        graphs_ok = (self.use_cuda_graphs and mode != 2 and cap >= 8 and _lib.profile is None and ops.gemm_profile is None)
-        steps_run = 0
-        buf_ver = (getattr(self.decoder, "buf_version", 0), id(self.decoder._packed)) if use_dec else None
-        for i in range(cap):
-            cur = i & 1
-            if graphs_ok and i >= 2:
-                if st.get("graph_buf_ver") != buf_ver:   # decoder buffers / packed weights were re-created: captured pointers are stale
-                    st["graphs"].clear()
-                    st["graph_buf_ver"] = buf_ver
-                g = st["graphs"].get(cur)
-                if g is None:      # capture this parity once (steps 2 and 3); nothing executes during capture, so replay right after
-                    step_dev.fill_(i)
-                    g = torch.cuda.CUDAGraph()
-                    cs = self._capture_stream(dev)
-                    cs.wait_stream(torch.cuda.current_stream())
-                    before = ops.launch_counter[0]
-                    with torch.cuda.stream(cs):
-                        g.capture_begin()
-                        step_body(i, cur, step_dev)
-                        g.capture_end()
-                    torch.cuda.current_stream().wait_stream(cs)
-                    st["graph_launches"][cur] = ops.launch_counter[0] - before
-                    ops.launch_counter[0] = before
-                    st["graphs"][cur] = g
-                elif i == 2:
-                    step_dev.fill_(i)  # graphs cached from an earlier call: (re)position the device step counter
-                g.replay()
-                ops.launch_counter[0] += st["graph_launches"][cur]
-            else:
-                step_body(i, cur, None)
-            steps_run = i + 1
-            if (i + 1) % check_every == 0 or end_detect:
-                call("espb_count_active_i32", ptr(active[(i + 1) & 1]), n, ptr(st["n_active"]))
-                _count()
-                if int(st["n_active"].item()) == 0:
-                    break
-        if side is not None:
-            torch.cuda.current_stream().wait_stream(side)
-        return self._collect(U, W, steps_run, maxlen, st["bp_parent"], st["bp_token"], st["e_count"], st["e_step"], st["e_slot"],
-                             st["e_score"], st["e_dec"], st["e_ctc"])
+    def _group_stream(self, dev, g):
+        key = (str(dev), g)
+        if not hasattr(self, "_grp_streams"):
+            self._grp_streams = {}
+        if key not in self._grp_streams:
+            self._grp_streams[key] = torch.cuda.Stream(device=dev)
+        return self._grp_streams[key]
 
     def _capture_stream(self, dev):
         if not hasattr(self, "_cap_streams"):
@@ -251,8 +181,8 @@ class BatchBeamSearch(torch.nn.Module):
             self._cap_streams[key] = torch.cuda.Stream(device=dev)
         return self._cap_streams[key]
 
-    def _side_stream(self, dev):
-        key = str(dev)
+    def _side_stream(self, dev, g=0):
+        key = (str(dev), g)
         if not hasattr(self, "_streams"):
             self._streams = {}
         if key not in self._streams:
@@ -317,3 +247,172 @@ class BatchBeamSearch(torch.nn.Module):
         if not res and minlenratio >= 0.1:  # beam_search.py:462-471
             return self.forward(x, maxlenratio, max(0.0, minlenratio - 0.1))
         return res
+
+
+class _SearchRun:
+    """State and step function of one group of utterances (one stream).  Created by BatchBeamSearch.forward_batch."""
+
+    def __init__(self, bs, g, stream, enc, enc_lens, enc_split, maxlenratio, minlenratio):
+        self.bs, self.g, self.stream = bs, g, stream
+        dev = enc.device
+        U, Tmax, D = enc.shape
+        W, V = bs.beam_size, bs.n_vocab
+        n = U * W
+        lens_cpu = enc_lens.detach().cpu().to(torch.int64)
+        if maxlenratio == 0:
+            maxlen = lens_cpu.clone()
+        elif maxlenratio < 0:
+            maxlen = torch.full_like(lens_cpu, -int(maxlenratio))
+        else:
+            maxlen = torch.clamp((maxlenratio * lens_cpu.double()).long(), min=1)
+        minlen = torch.full_like(lens_cpu, -int(minlenratio)) if minlenratio < 0 else (minlenratio * lens_cpu.double()).long()
+        cap = int(maxlen.max())
+        if enc_split is None:
+            enc_split = ops.split_from(enc.contiguous().view(U * Tmax, D))
+        use_dec, use_ctc = bs.decoder is not None, bs.ctc is not None
+        mode = 1 if (use_dec and use_ctc) else (0 if use_dec else 2)
+        P = bs.pre_beam_size if mode == 1 else W
+        st = bs._state(dev, U, Tmax, W, V, cap, mode, P, g)
+        self.U, self.W, self.V, self.n, self.Tmax, self.cap, self.mode, self.P, self.st = U, W, V, n, Tmax, cap, mode, P, st
+        self.maxlen, self.use_dec, self.use_ctc, self.dev = maxlen, use_dec, use_ctc, dev
+        self.finished, self.steps_run = False, 0
+
+        # ---- (re)initialise the state in place: one hypothesis [sos] per utterance (batch_beam_search.py:124-153)
+        for k in ("score", "sc_dec", "sc_ctc", "active"):
+            st[k][0].zero_(); st[k][1].zero_()
+        st["active"][0].view(U, W)[:, 0] = 1
+        st["last_tok"][0].fill_(bs.sos); st["last_tok"][1].fill_(bs.sos)
+        st["bp_parent"].fill_(-1); st["bp_token"].fill_(bs.eos)
+        st["e_count"].zero_(); st["done"].zero_()
+        st["best_at"].fill_(float("-inf")); st["best_all"].fill_(float("-inf"))
+        st["lens32"].copy_(lens_cpu.to(torch.int32)); st["maxlen"].copy_(maxlen.to(torch.int32)); st["minlen"].copy_(minlen.to(torch.int32))
+        st["step"].zero_()
+        self.lens32 = st["lens32"]
+        self.dst = None
+        if use_dec:
+            bs.decoder.ws_tag = g
+            self.dst = bs.decoder.init_memory(enc_split, U, Tmax, self.lens32, n, cap)
+        self.logp_ctc = self.logp_tok = None
+        self.tok_major = 0
+        if use_ctc:
+            self.logp_ctc = bs.ctc.log_softmax(enc, enc_split, out=st["logp_ctc"])   # (U, Tmax, V), scorers/ctc.py:96-99
+            call("espb_ctc_init_state_f32", ptr(self.logp_ctc), U, Tmax, V, ptr(self.lens32), 0, W, ptr(st["r"][0]), ptr(st["s_prev"][0]))
+            _count()
+            self.logp_tok = self.logp_ctc
+            if mode == 1:   # token-major copy [U][V][Tmax]: the per-step candidate columns become contiguous reads
+                self.logp_tok, self.tok_major = st["logp_ctc_t"], 1
+                call("espb_transpose_tv_f32", ptr(self.logp_ctc), U, Tmax, V, ptr(self.logp_tok))
+                _count()
+        self.end_detect = 1 if maxlenratio == 0.0 else 0
+        self.side = bs._side_stream(dev, g) if (use_ctc and use_dec) else None
+        self.buf_ver = (getattr(bs.decoder, "buf_version", 0), id(bs.decoder._packed)) if use_dec else None
+
+    def step_body(self, i, cur, sp):
+        """One search step. `sp` is None (host step index i) or the device step counter (graph mode: i is ignored)."""
+        bs, st = self.bs, self.st
+        U, W, V, n, Tmax, P, mode, cap = self.U, self.W, self.V, self.n, self.Tmax, self.P, self.mode, self.cap
+        lens32, side = self.lens32, self.side
+        score, sc_dec, sc_ctc, active, last_tok = st["score"], st["sc_dec"], st["sc_ctc"], st["active"], st["last_tok"]
+        parent, anc = st["parent"], st["anc"]
+        r, s_prev = st.get("r"), st.get("s_prev")
+        nxt = cur ^ 1
+        iv = 0 if sp is not None else i
+        main = torch.cuda.current_stream()
+        forked = False
+        if self.use_ctc and (sp is not None or i >= 1):
+            # CTC forward variables of the hypotheses chosen in the previous step (scorers/ctc.py:40-63): only the scoring below needs
+            # them, so the T-step recursion runs on a side stream concurrently with the decoder pass
+            def advance():
+                call("espb_ctc_advance_f32", ptr(self.logp_tok), U, Tmax, V, ptr(lens32), 0, bs.eos, W, ptr(r[nxt]), ptr(parent),
+                     ptr(last_tok[nxt]), ptr(last_tok[cur]), ptr(active[cur]), iv - 1, ptr(sp), ptr(r[cur]), ptr(s_prev[cur]), self.tok_major)
+                _count()
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    advance()
+                forked = True
+            else:
+                advance()
+        logp_dec = None
+        if self.use_dec:
+            bs.decoder.ws_tag = self.g
+            logp_dec = bs.decoder.step(self.dst, iv, last_tok[cur], anc[cur], W, sp)
+        if forked:
+            main.wait_stream(side)
+        if mode == 1:
+            ops.rows_topk(logp_dec, bs.w_dec, P, st["cand_ids"], st["cand_val"])
+            call("espb_ctc_score_cands_f32", ptr(self.logp_tok), U, Tmax, V, ptr(lens32), 0, bs.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
+                 ptr(last_tok[cur]), iv, ptr(sp), ptr(st["cand_ids"]), P, ptr(st["part"]), ptr(st["psi"]), ptr(st["valid"]), self.tok_major)
+            _count()
+        elif mode == 0:
+            ops.rows_topk(logp_dec, bs.w_dec, P, st["cand_ids"], st["cand_val"])
+        else:
+            call("espb_ctc_score_dense_f32", ptr(self.logp_ctc), U, Tmax, V, ptr(lens32), 0, bs.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
+                 ptr(last_tok[cur]), i, ptr(st["part"]))
+            _count()
+            ops.rows_topk(st["part"], bs.w_ctc, P, st["cand_ids"], st["cand_val"])
+        call("espb_beam_select", ptr(score[cur]), ptr(sc_dec[cur]), ptr(sc_ctc[cur]), ptr(active[cur]), ptr(score[nxt]),
+             ptr(sc_dec[nxt]), ptr(sc_ctc[nxt]), ptr(active[nxt]), ptr(last_tok[nxt]), ptr(parent), ptr(st["bp_parent"]),
+             ptr(st["bp_token"]), ptr(st["e_count"]), ptr(st["e_step"]), ptr(st["e_slot"]), ptr(st["e_score"]), ptr(st["e_dec"]),
+             ptr(st["e_ctc"]), st["ended_cap"], ptr(st["best_at"]), ptr(st["best_all"]), ptr(st["done"]), U, W, P, V, iv, ptr(sp),
+             ptr(st["maxlen"]), ptr(st["minlen"]), bs.eos, bs.w_dec, bs.w_ctc, bs.penalty, mode, ptr(st["cand_ids"]),
+             ptr(st["cand_val"]), ptr(logp_dec), ptr(st.get("part")), ptr(st.get("valid")), self.end_detect, cap)
+        _count()
+        if self.use_dec:
+            call("espb_anc_update_i32", ptr(anc[cur]), ptr(anc[nxt]), cap + 1, ptr(parent), iv, ptr(sp), n)
+            _count()
+        if sp is not None:
+            call("espb_step_inc_i32", ptr(sp))
+            _count()
+
+    def step(self, i):
+        from . import lib as _lib
+
+        bs, st = self.bs, self.st
+        step_dev = st["step"]
+        graphs_ok = (bs.use_cuda_graphs and self.mode != 2 and self.cap >= 8 and _lib.profile is None and ops.gemm_profile is None)
+        cur = i & 1
+        if graphs_ok and i >= 2:
+            if st.get("graph_buf_ver") != self.buf_ver:   # decoder buffers / packed weights were re-created: captured pointers are stale
+                st["graphs"].clear()
+                st["graph_buf_ver"] = self.buf_ver
+            g = st["graphs"].get(cur)
+            if g is None:      # capture this parity once (steps 2 and 3); nothing executes during capture, so replay right after
+                step_dev.fill_(i)
+                g = torch.cuda.CUDAGraph()
+                cs = bs._capture_stream(self.dev)
+                cs.wait_stream(torch.cuda.current_stream())
+                before = ops.launch_counter[0]
+                with torch.cuda.stream(cs):
+                    g.capture_begin()
+                    self.step_body(i, cur, step_dev)
+                    g.capture_end()
+                torch.cuda.current_stream().wait_stream(cs)
+                st["graph_launches"][cur] = ops.launch_counter[0] - before
+                ops.launch_counter[0] = before
+                st["graphs"][cur] = g
+            elif i == 2:
+                step_dev.fill_(i)  # graphs cached from an earlier call: (re)position the device step counter
+            g.replay()
+            ops.launch_counter[0] += st["graph_launches"][cur]
+        else:
+            self.step_body(i, cur, None)
+        self.steps_run = i + 1
+
+    def poll(self, i):
+        st = self.st
+        call("espb_count_active_i32", ptr(st["active"][(i + 1) & 1]), self.n, ptr(st["n_active"]))
+        _count()
+        if int(st["n_active"].item()) == 0:
+            self.finished = True
+
+    def join(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+
+    def collect(self):
+        st = self.st
+        return self.bs._collect(self.U, self.W, self.steps_run, self.maxlen, st["bp_parent"], st["bp_token"], st["e_count"], st["e_step"],
+                                st["e_slot"], st["e_score"], st["e_dec"], st["e_ctc"])

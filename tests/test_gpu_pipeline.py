@@ -315,3 +315,30 @@ def test_speech2text_with_global_mvn_vs_oracle(tmp_path):
     fn = OF.global_mvn(feats[None], torch.tensor([feats.shape[0]]), mean, std)[0]
     ref = OE.conformer_encode(fn, w, cfg["heads"], cfg["enc_layers"])
     assert _maxerr(enc[0, : ref.shape[0]], ref) < 2e-3
+
+
+@pytest.mark.parametrize("groups", [2, 3])
+def test_utterance_groups_on_streams_match_single_group(groups):
+    """Large batches are searched as independent utterance groups on separate streams (own state / workspace / CUDA graphs);
+    the n-best lists must be those of the single-group search, and of the oracle."""
+    cfg = dict(d_model=64, heads=4, ff=128, enc_layers=2, dec_layers=2, vocab=60, kernel=15)
+    w = random_weights(cfg, seed=7)
+    kw = dict(beam_size=5, ctc_weight=0.3, maxlenratio=-12.0, nbest=5)
+    s2t = speech2text(cfg, w, **kw)
+    lens = [16000, 9000, 12345, 14000, 8000, 15000, 10000]
+    waves = [refbuild.waveform(70 + i, n) for i, n in enumerate(lens)]
+    bs = s2t.beam_search
+    bs.group_min_utts, bs.n_groups = 10 ** 9, 1
+    single = s2t.batch_decode(waves)
+    bs.group_min_utts, bs.n_groups = 2, groups
+    for _ in range(2):   # second call replays the groups' cached CUDA graphs
+        grouped = s2t.batch_decode(waves)
+        assert len(grouped) == len(single) == len(waves)
+        for a, b in zip(grouped, single):
+            assert [h[3].yseq.tolist() for h in a] == [h[3].yseq.tolist() for h in b]
+            for ha, hb in zip(a, b):
+                assert abs(ha[3].score - hb[3].score) <= 1e-5 * max(1.0, abs(hb[3].score))
+    o = oracle.OracleSpeech2Text(cfg, w, **kw)
+    for i in (0, 4, 6):
+        ref = o(waves[i])
+        assert [h[3].yseq.tolist() for h in grouped[i]] == [h[3].yseq.tolist() for h in ref]
