@@ -98,3 +98,14 @@ if which in ("ln", "all"):
         e1.record(s)
         s.synchronize()
     print(f"[kernel_microbench] layernorm {rows}x{D} in-graph back-to-back: {e0.elapsed_time(e1) * 1e3 / 500:6.2f} us/launch")
+
+if which in ("ffn", "all"):
+    from espnet_b200 import ops
+
+    M, N, K = 59968, 2048, 512      # encoder feed-forward w_1 of the 64 x 30 s workload (Swish, hi/lo split output)
+    a, b = ops.split_from(torch.randn(M, K, device=dev)), ops.split_from(torch.randn(N, K, device=dev) / K ** 0.5)
+    bias = torch.randn(N, device=dev)
+    out = torch.empty(2, M, N, device=dev)
+    alg_bytes = (2 * M * K + 2 * N * K + 2 * M * N) * 4
+    timeit(f"gemm_tf32x3_2cta M{M} N{N} K{K} swish split ({2.0 * M * N * K / 1e12:.3f} TFLOP algorithmic)",
+           lambda: ops.linear(a, b, out, bias=bias, act=ops.ACT_SWISH, split_out=True), alg_bytes)
