@@ -198,6 +198,14 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------- espnet_b200 arm
+# DRAM traffic of ONE launch of the dominant kernel, from the committed `ncu --set full` capture (scripts/gpu_ncu_micro.sh ffn 2cta):
+# the encoder feed-forward w_1 GEMM of this workload (M 59968, N 2048, K 512, Swish, hi/lo split output).  dram__bytes_read.sum +
+# dram__bytes_write.sum; the algorithmic bytes are the hi/lo A and B planes read once and the hi/lo C planes written once.
+NCU_TRAFFIC = {"launch": "gemm_tf32x3_2cta_kernel<256,3,swish,split> M59968 N2048 K512", "dram_bytes": 275.803136e6 + 959.088128e6,
+               "algorithmic_bytes": (2 * 59968 * 512 + 2 * 2048 * 512 + 2 * 59968 * 2048) * 4.0, "gpu_time_us_under_ncu": 627.264,
+               "tensor_pipe_active_pct": 61.13, "source": "profiles/r01_ncu_gemm_2cta_ffn_w1_summary.txt"}
+
+
 def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
 
@@ -371,10 +379,11 @@ def run_b200(args, rank, local_rank, world):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_tf32x3_2cta_kernel (all its launches in one step: encoder, CTC head, decoder memory)", "achieved": ach, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
+                     "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": NCU_TRAFFIC["dram_bytes"], "traffic_launch": NCU_TRAFFIC,
+                     "peak_source": peak_src,
                      "launches": len(big), "gemm_ms_per_step": g_ms, "algorithmic_tflop_per_step": g_flops / 1e12,
                      "frac_of_3xtf32_ceiling": (ach / (peak_tf / 6.0)) if peak_tf else None,
-                     "decode_gemm_1cta": {"kernel": "gemm_tf32x3_kernel", "launches": len(small), "ms_per_step_ungraphed": s_ms,
+                     "decode_gemm_1cta": {"kernel": "gemm_tf32x3_sk_kernel / gemm_tf32x3_mc_kernel / gemm_tf32x3_kernel (128-row 1-CTA tiles)", "launches": len(small), "ms_per_step_ungraphed": s_ms,
                                           "achieved": (s_flops / (s_ms / 1000.0) / 1e12) if s_ms > 0 else None},
                      "note": "algorithmic FLOPs (2MNK); each is executed as 3 tf32 MMAs at half the bf16 rate, so 1/6 of the bf16 peak is the ceiling of this formulation"},
     }
