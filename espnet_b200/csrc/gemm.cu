@@ -726,7 +726,7 @@ __device__ __forceinline__ float acc_at(const float (&acc)[N], int idx) {
 }
 
 // ACT / SPLIT are compile-time so that the 128-bit epilogue path carries no per-element branches.
-template <int BN, int STAGES, int ACT, bool SPLIT>
+template <int BN, int STAGES, int ACT, bool SPLIT, bool PLAIN>   // PLAIN: no bias / residual / scaling (the attention score and context products)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
 gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym, int axm, int aym) {
   constexpr int BH = BN / 2;                      // B rows staged by each CTA
@@ -899,10 +899,39 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         for (int j = 0; j < CW / 32; ++j) {
           const int colb = n0 + half * CW + j * 32;
           if (row0 >= p.M || colb >= Ncols) continue;          // warp-uniform: block entirely outside the matrix
+          if (PLAIN && row0 + 32 <= p.M && colb + 32 <= Ncols) {
+            // interior block of a product without bias / residual / scaling (attention scores, context): straight-line transpose + stores,
+            // no per-row or per-column predicates (the generic path below spends most of its issue slots on them)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              __syncwarp();
+              if ((lane >> 4) == hh) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<float4*>(wrow + i) = make_float4(acc[j * 32 + i], acc[j * 32 + i + 1], acc[j * 32 + i + 2], acc[j * 32 + i + 3]);
+              }
+              __syncwarp();
+              float* cpi = crow0 + (long long)(hh * 16) * ldc + colb + c4;
+#pragma unroll 2
+              for (int it = 0; it < 4; ++it, cpi += 4 * ldc) {
+                const float4 v = *reinterpret_cast<const float4*>(rbase + it * 4 * 36);
+                if (SPLIT) {
+                  float4 h, l;
+                  h.x = espb::tf32_hi(v.x); h.y = espb::tf32_hi(v.y); h.z = espb::tf32_hi(v.z); h.w = espb::tf32_hi(v.w);
+                  l.x = espb::tf32_lo(v.x, h.x); l.y = espb::tf32_lo(v.y, h.y); l.z = espb::tf32_lo(v.z, h.z); l.w = espb::tf32_lo(v.w, h.w);
+                  *reinterpret_cast<float4*>(cpi) = h;
+                  *reinterpret_cast<float4*>(cpi + cpl) = l;
+                } else {
+                  *reinterpret_cast<float4*>(cpi) = v;
+                }
+              }
+            }
+            continue;
+          }
           const int col = colb + c4;
           const bool c_full = col + 3 < Ncols, c_part = !c_full && col < Ncols;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_b && c_full) b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col));
+          if (!PLAIN && has_b && c_full) b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col));
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             __syncwarp();
@@ -917,7 +946,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (has_r && c_full && hh * 16 + it * 4 < rows_left)
+              if (!PLAIN && has_r && c_full && hh * 16 + it * 4 < rows_left)
                 rv[it] = *reinterpret_cast<const float4*>(rrow0 + (long long)(hh * 16 + it * 4) * ldr + col);
             }
 #pragma unroll
@@ -927,14 +956,17 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
               const float4 v = *reinterpret_cast<const float4*>(rbase + it * 4 * 36);
               float* cpi = cp + (long long)(it * 4) * ldc;
               if (c_full) {
-                float t[4] = {v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w};
-                const float rr4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
+                float t[4] = {v.x, v.y, v.z, v.w};
+                if (!PLAIN) {
+                  const float bb4[4] = {b4.x, b4.y, b4.z, b4.w};
+                  const float rr4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float x = t[i];
-                  if (ACT == espb::ACT_RELU) x = fmaxf(x, 0.f);
-                  else if (ACT == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
-                  t[i] = fmaf(alpha, x, rr4[i]);
+                  for (int i = 0; i < 4; ++i) {
+                    float x = t[i] + bb4[i];
+                    if (ACT == espb::ACT_RELU) x = fmaxf(x, 0.f);
+                    else if (ACT == espb::ACT_SWISH) x = __fdividef(x, 1.f + __expf(-x));
+                    t[i] = fmaf(alpha, x, rr4[i]);
+                  }
                 }
                 if (SPLIT) {
                   float4 h, l;
@@ -1133,14 +1165,14 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc
   return ESPB_OK;
 }
 
-template <int BN, int STAGES, int ACT, bool SPLIT>
+template <int BN, int STAGES, int ACT, bool SPLIT, bool PLAIN>
 int launch_tc2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
   constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * (BN / 2) * 128) + 8 * 16 * 36 * 4 + 1024 + 16 * STAGES + 64;
   static_assert(smem <= 232448, "dynamic shared memory budget exceeded");
   static bool attr_set = false;
   static int num_sms = 0;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tf32x3_2cta_kernel<BN, STAGES, ACT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tf32x3_2cta_kernel<BN, STAGES, ACT, SPLIT, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       espb_set_error("cudaFuncSetAttribute(max dynamic smem) failed");
       return ESPB_ERR_CUDA;
     }
@@ -1152,7 +1184,7 @@ int launch_tc2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmD
   const long long tiles = (long long)((d.M + 255) / 256) * ((d.N + BN - 1) / BN) * d.nbx * d.nby;
   const long long pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;   // persistent: one CTA pair per SM pair
   dim3 grid((unsigned)(2 * pairs), 1, 1);
-  gemm_tf32x3_2cta_kernel<BN, STAGES, ACT, SPLIT><<<grid, V2_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
+  gemm_tf32x3_2cta_kernel<BN, STAGES, ACT, SPLIT, PLAIN><<<grid, V2_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
@@ -1160,13 +1192,18 @@ int launch_tc2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmD
 template <int BN, int STAGES>
 int launch_tc2(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
   const int v = d.act * 2 + (d.split_out ? 1 : 0);
+  const bool plain = d.act == espb::ACT_NONE && d.bias == nullptr && d.R == nullptr && d.alpha == 1.0f && !getenv("ESPB_GEMM_NO_PLAIN");
+  if (plain) {
+    if (d.split_out) return launch_tc2_v<BN, STAGES, espb::ACT_NONE, true, true>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    return launch_tc2_v<BN, STAGES, espb::ACT_NONE, false, true>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+  }
   switch (v) {
-    case 0: return launch_tc2_v<BN, STAGES, espb::ACT_NONE, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
-    case 1: return launch_tc2_v<BN, STAGES, espb::ACT_NONE, true>(tmA, tmB, d, bxm, bym, axm, aym, stream);
-    case 2: return launch_tc2_v<BN, STAGES, espb::ACT_RELU, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
-    case 3: return launch_tc2_v<BN, STAGES, espb::ACT_RELU, true>(tmA, tmB, d, bxm, bym, axm, aym, stream);
-    case 4: return launch_tc2_v<BN, STAGES, espb::ACT_SWISH, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
-    case 5: return launch_tc2_v<BN, STAGES, espb::ACT_SWISH, true>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 0: return launch_tc2_v<BN, STAGES, espb::ACT_NONE, false, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 1: return launch_tc2_v<BN, STAGES, espb::ACT_NONE, true, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 2: return launch_tc2_v<BN, STAGES, espb::ACT_RELU, false, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 3: return launch_tc2_v<BN, STAGES, espb::ACT_RELU, true, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 4: return launch_tc2_v<BN, STAGES, espb::ACT_SWISH, false, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    case 5: return launch_tc2_v<BN, STAGES, espb::ACT_SWISH, true, false>(tmA, tmB, d, bxm, bym, axm, aym, stream);
     default: espb_set_error("gemm: unknown activation"); return ESPB_ERR_ARG;
   }
 }

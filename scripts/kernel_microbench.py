@@ -109,3 +109,17 @@ if which in ("ffn", "all"):
     alg_bytes = (2 * M * K + 2 * N * K + 2 * M * N) * 4
     timeit(f"gemm_tf32x3_2cta M{M} N{N} K{K} swish split ({2.0 * M * N * K / 1e12:.3f} TFLOP algorithmic)",
            lambda: ops.linear(a, b, out, bias=bias, act=ops.ACT_SWISH, split_out=True), alg_bytes)
+
+if which in ("ac", "all"):
+    from espnet_b200 import ops
+
+    # q_u . k^T of the rel-pos attention (encoder.py): per (utterance, head) a T x T x 64 product, operands are head slices of [M][D] / [M][3D]
+    B, H, T, D = 64, 8, 937, 512
+    dk, Tp, M = D // H, 960, 64 * 937
+    qu = ops.split_from(torch.randn(M, D, device=dev))
+    qkv = ops.split_from(torch.randn(M, 3 * D, device=dev))
+    ac = torch.empty(B * H * T, Tp, device=dev)
+    alg = (2 * M * D * 2 + B * H * T * T) * 4        # hi/lo q and k read once, scores written once
+    timeit(f"q_u.k^T GEMM T{T} x T{T} x {dk}, {B * H} problems ({2.0 * B * H * T * T * dk / 1e12:.3f} TFLOP algorithmic)",
+           lambda: ops.gemm(T, T, dk, qu, M * D, D, qkv, M * 3 * D, 3 * D, ac, Tp, nbx=H, nby=B, sa=(dk, T * D), sb=(dk, T * 3 * D),
+                            sc=(T * Tp, H * T * Tp), b_off=D), alg)
