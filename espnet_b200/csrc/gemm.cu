@@ -1278,12 +1278,13 @@ int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version)
   const long long tiles_m = (d.M + BM - 1) / BM, nb = (long long)d.nbx * d.nby;
   if (version == 2 && (long long)d.M * d.nbx * d.nby > 1024) {   // tiny (decode-step) problems are latency-bound: 128x64 1-CTA tiles spread them over more SMs
     // CTA-pair kernel: 256 x BN tiles; B box = BN/2 rows per CTA
-    const int bn = (d.N <= 128) ? 128 : 256;
+    const int bn = (d.N <= 64 && !getenv("ESPB_GEMM_NO_BN64")) ? 64 : (d.N <= 128) ? 128 : 256;   // N = d_k products (p.v, decoder memory K/V) waste no MMA columns
     long long dims[5] = {d.K, d.N, bxm ? d.nbx : 1, bym ? d.nby : 1, 2};
     long long str[4] = {d.ldb, d.sb_x, d.sb_y, d.b_plane};
     rc = make_map(&tmB, d.B, dims, str, bn / 2);
     if (rc != ESPB_OK) return rc;
     if (bn == 256) return launch_tc2<256, 3>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+    if (bn == 64) return launch_tc2<64, 5>(tmA, tmB, d, bxm, bym, axm, aym, stream);
     return launch_tc2<128, 4>(tmA, tmB, d, bxm, bym, axm, aym, stream);
   }
   if (version == 2 && nb == 1 && d.a_mode == 0 && d.band_t == 0 && d.kob == 0 && d.N > 64 && splitk_enabled()) {

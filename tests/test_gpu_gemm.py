@@ -39,7 +39,9 @@ def _tol(mode, K, scale=1.0, M=None):
 SHAPES = [(2000, 512, 2048), (1500, 1536, 512), (128, 64, 32), (128, 256, 64), (200, 130, 96), (640, 512, 512), (937, 512, 2048), (22, 50, 64), (300, 5000, 64),
           (1000, 1536, 512), (129, 65, 33 * 4),
           # decode-step shapes: K split 4-way / 2-way over a cluster (ragged last slice, N overhang), A-multicast tiles
-          (640, 512, 2048), (640, 1536, 512), (100, 200, 300), (50, 129, 9 * 32), (640, 2048, 512), (320, 5000, 512)]
+          (640, 512, 2048), (640, 1536, 512), (100, 200, 300), (50, 129, 9 * 32), (640, 2048, 512), (320, 5000, 512),
+          # CTA-pair kernel with 64-column tiles (N <= d_k = 64): column overhang and a K tail (K must stay a multiple of 4: TMA strides)
+          (1500, 48, 520)]
 
 
 @pytest.mark.parametrize("mode", MODES)
