@@ -23,6 +23,7 @@ from .decoder import TransformerDecoder
 from .encoder import ConformerEncoder
 from .errors import TooShortUttError  # noqa: F401
 from .frontend import DefaultFrontend, GlobalMVN, UtteranceMVN
+from .text import TokenIDConverter, tokenizer_for_inference
 from .search import BatchBeamSearch, Hypothesis
 
 logger = logging.getLogger(__name__)
@@ -32,21 +33,6 @@ frontend_choices = {"default": DefaultFrontend}
 normalize_choices = {"global_mvn": GlobalMVN, "utterance_mvn": UtteranceMVN}
 encoder_choices = {"conformer": ConformerEncoder}
 decoder_choices = {"transformer": TransformerDecoder}
-
-
-class TokenIDConverter:
-    """ids2tokens / tokens2ids subset of espnet2/text/token_id_converter.py:8-59."""
-
-    def __init__(self, token_list, unk_symbol="<unk>"):
-        self.token_list = list(token_list)
-        self.token2id = {t: i for i, t in enumerate(self.token_list)}
-        self.unk_id = self.token2id.get(unk_symbol, 1)
-
-    def ids2tokens(self, ids):
-        return [self.token_list[i] for i in ids]
-
-    def tokens2ids(self, tokens):
-        return [self.token2id.get(t, self.unk_id) for t in tokens]
 
 
 class ESPnetASRModel(torch.nn.Module):
@@ -120,8 +106,8 @@ class Speech2Text:
     def __init__(self, asr_train_config=None, asr_model_file=None, device: str = "cuda", dtype: str = "float32",
                  beam_size: int = 20, ctc_weight: float = 0.5, lm_weight: float = 1.0, ngram_weight: float = 0.9,
                  penalty: float = 0.0, nbest: int = 1, maxlenratio: float = 0.0, minlenratio: float = 0.0,
-                 normalize_length: bool = False, batch_size: int = 1, asr_model: Optional[ESPnetASRModel] = None,
-                 asr_train_args=None, **unused):
+                 normalize_length: bool = False, batch_size: int = 1, token_type: Optional[str] = None, bpemodel: Optional[str] = None,
+                 asr_model: Optional[ESPnetASRModel] = None, asr_train_args=None, **unused):
         if dtype != "float32":
             raise NotImplementedError("espnet_b200 computes in float32 (the reference's inference dtype)")
         if not str(device).startswith("cuda"):
@@ -141,7 +127,8 @@ class Speech2Text:
                                            token_list=token_list, pre_beam_score_key=None if ctc_weight == 1.0 else "full",
                                            normalize_length=normalize_length)
         self.converter = TokenIDConverter(token_list)
-        self.tokenizer = None
+        self.tokenizer = tokenizer_for_inference(token_type, bpemodel, asr_train_args)   # asr_inference.py:395-430
+        logger.info(f"Text tokenizer: {self.tokenizer}")
 
     def _to_batch(self, speeches: Sequence[Union[torch.Tensor, np.ndarray]]):
         lens = torch.tensor([int(s.shape[0]) for s in speeches], dtype=torch.long)
@@ -151,7 +138,23 @@ class Speech2Text:
             host[i, : lens[i]] = torch.as_tensor(s, dtype=torch.float32)
         return host.to(self.device, non_blocking=True), lens
 
+    def _log_best(self, nbest_hyps: List[Hypothesis]):
+        """End-of-search log lines of beam_search.py:460-487 (utils/calculate_rtf.py pairs 'speech length' with 'best hypo')."""
+        if not nbest_hyps:
+            logger.warning("there is no N-best results")
+            return
+        best = nbest_hyps[0]
+        w = self.beam_search.weights
+        for k, v in best.scores.items():
+            logger.info(f"{v:6.2f} * {w.get(k, 0.0):3} = {v * w.get(k, 0.0):6.2f} for {k}")
+        logger.info(f"total log probability: {float(best.score):.2f}")
+        logger.info(f"normalized log probability: {float(best.score) / len(best.yseq):.2f}")
+        logger.info(f"total number of ended hypotheses: {len(nbest_hyps)}")
+        logger.info("best hypo: " + "".join(self.converter.token_list[x] for x in best.yseq[1:-1].tolist()) + "\n")
+
     def _results(self, nbest_hyps: List[Hypothesis]):
+        if logger.isEnabledFor(logging.INFO):
+            self._log_best(nbest_hyps)
         results = []
         for hyp in nbest_hyps[: self.nbest]:
             token_int = hyp.yseq[1:-1].tolist()                       # asr_inference.py:659-666

@@ -66,6 +66,7 @@ _SIGS = {
     "espb_count_active_i32": [P, I, P, P],
 }
 
+ABI_VERSION = 2   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["espb_last_error", "espb_abi_version", "espb_device_sm", "espb_frontend_blocks"])
 
 
@@ -90,6 +91,9 @@ def load():
     lib.espb_last_error.restype = ctypes.c_char_p
     lib.espb_last_error.argtypes = []
     lib.espb_abi_version.restype = c_int
+    if lib.espb_abi_version() != ABI_VERSION:
+        raise LibraryMissing(f"{LIB_PATH} has ABI version {lib.espb_abi_version()}, this package binds version {ABI_VERSION}: rebuild it "
+                             "(`make -C espnet_b200/csrc`)")
     lib.espb_frontend_blocks.argtypes = [c_int]
     lib.espb_frontend_blocks.restype = c_int
     lib.espb_device_sm.argtypes = [POINTER(c_int), POINTER(c_int)]

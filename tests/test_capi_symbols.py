@@ -31,7 +31,30 @@ def test_library_exports_every_declared_symbol():
     for sym in _header_symbols():
         assert hasattr(handle, sym), sym
     handle.espb_abi_version.restype = ctypes.c_int
-    assert handle.espb_abi_version() == 1
+    from espnet_b200 import lib as _l
+
+    assert handle.espb_abi_version() == _l.ABI_VERSION == 2
+
+
+def test_binding_arity_matches_header():
+    """Every ctypes signature in lib._SIGS has as many arguments as the C prototype in include/espnet_b200.h (incl. the stream)."""
+    from espnet_b200 import lib
+
+    src = open(os.path.join(ROOT, "include", "espnet_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = dict(re.findall(r"\bint\s+(espb_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S))
+    for name, sig in lib._SIGS.items():
+        assert name in protos, name
+        params = [a for a in protos[name].split(",") if a.strip() and a.strip() != "void"]
+        assert len(params) == len(sig), (name, len(params), len(sig))
+        assert "cudaStream_t" in params[-1], name
+        for c_arg, ct in zip(params, sig):   # pointers bind to c_void_p, scalars to the matching ctypes scalar
+            is_ptr = "*" in c_arg or "cudaStream_t" in c_arg
+            binds_ptr = ct is ctypes.c_void_p or issubclass(ct, ctypes._Pointer)
+            assert is_ptr == binds_ptr, (name, c_arg, ct)
+            if not is_ptr:
+                want = ctypes.c_longlong if "long long" in c_arg else ctypes.c_float if "float" in c_arg else ctypes.c_int
+                assert ct is want, (name, c_arg, ct)
 
 
 def test_ops_refuse_cpu_tensors():

@@ -1,0 +1,88 @@
+"""Output-side text conversion (host only) against the reference's own classes (tests/golden/text.json, made by
+tests/golden/make_golden_text.py from espnet2/text/*) and against sentencepiece itself for the bpe tokenizer."""
+import argparse
+import json
+import os
+
+import pytest
+
+from espnet_b200.text import TokenIDConverter, build_tokenizer, tokenizer_for_inference
+
+G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "text.json"), encoding="utf-8"))
+
+
+def test_token_id_converter_matches_reference():
+    conv = TokenIDConverter(G["token_list"])
+    assert conv.ids2tokens(G["ids"]) == G["tokens"]
+    assert conv.tokens2ids(G["tokens"] + ["zzz"]) == G["back"]        # unknown token -> <unk>
+    assert conv.get_num_vocabulary_size() == G["nvocab"]
+    with pytest.raises(RuntimeError):
+        TokenIDConverter(["a", "a", "<unk>"])                          # duplicated symbol (token_id_converter.py:36-38)
+    with pytest.raises(RuntimeError):
+        TokenIDConverter(["a", "b"])                                   # no <unk> (token_id_converter.py:41-45)
+
+
+def test_token_list_file(tmp_path):
+    f = tmp_path / "tokens.txt"
+    f.write_text("\n".join(G["token_list"]) + "\n", encoding="utf-8")
+    assert TokenIDConverter(str(f)).token_list == G["token_list"]
+
+
+def test_char_and_word_tokens2text_match_reference():
+    assert build_tokenizer("char").tokens2text(G["tokens"]) == G["char_text"]
+    assert build_tokenizer("char", space_symbol="a").tokens2text(G["tokens"]) == G["char_text_custom_space"]
+    assert build_tokenizer("word").tokens2text(["hello", "world", "<unk>"]) == G["word_text"]
+    assert build_tokenizer("word", delimiter="|").tokens2text(["hello", "world"]) == G["word_text_delim"]
+    assert repr(build_tokenizer("word")) == G["word_repr"]
+
+
+def test_bpe_tokens2text_is_sentencepiece_decode(tmp_path):
+    spm = pytest.importorskip("sentencepiece")
+    corpus = tmp_path / "corpus.txt"
+    corpus.write_text("\n".join(["hello world", "the quick brown fox", "jumps over the lazy dog", "hello there world"] * 20), encoding="utf-8")
+    spm.SentencePieceTrainer.train(input=str(corpus), model_prefix=str(tmp_path / "bpe"), vocab_size=40, model_type="bpe",
+                                   hard_vocab_limit=False, minloglevel=2)
+    model = str(tmp_path / "bpe.model")
+    sp = spm.SentencePieceProcessor()
+    sp.load(model)
+    pieces = sp.EncodeAsPieces("hello brown dog")
+    tok = build_tokenizer("bpe", model)
+    assert tok.tokens2text(pieces) == sp.DecodePieces(pieces) == "hello brown dog"
+    with pytest.raises(ValueError):
+        build_tokenizer("bpe", None)
+
+
+def test_inference_selection_rule():
+    """asr_inference.py:395-430: arguments override the training config; bpe without a model and token_type None give no tokenizer."""
+    args = argparse.Namespace(token_type="char", bpemodel=None)
+    assert type(tokenizer_for_inference(None, None, args)).__name__ == "CharTokenizer"
+    assert type(tokenizer_for_inference("word", None, args)).__name__ == "WordTokenizer"
+    assert tokenizer_for_inference(None, None, argparse.Namespace(token_type=None, bpemodel=None)) is None
+    assert tokenizer_for_inference(None, None, argparse.Namespace(token_type="bpe", bpemodel=None)) is None
+    assert tokenizer_for_inference(None, None, argparse.Namespace()) is None
+    with pytest.raises(NotImplementedError):
+        tokenizer_for_inference("phn", None, args)
+
+
+def test_end_of_search_log_lines(caplog):
+    """The lines utils/calculate_rtf.py keys on ('best hypo') and the score summary of beam_search.py:476-487."""
+    import logging
+    import types
+
+    import torch
+
+    import espnet_b200
+    from espnet_b200.search import Hypothesis
+
+    s2t = espnet_b200.Speech2Text.__new__(espnet_b200.Speech2Text)
+    s2t.converter = TokenIDConverter(G["token_list"])
+    s2t.beam_search = types.SimpleNamespace(weights=dict(decoder=0.7, ctc=0.3, length_bonus=0.0))
+    s2t.tokenizer, s2t.nbest = build_tokenizer("char"), 1
+    hyp = Hypothesis(yseq=torch.tensor([11, 3, 4, 2, 5, 11]), score=-3.25, scores=dict(decoder=-2.0, ctc=-6.0))
+    with caplog.at_level(logging.INFO, logger="espnet_b200.asr_inference"):
+        res = s2t._results([hyp])
+    assert res[0][0] == "ab c" and res[0][1] == ["a", "b", "<space>", "c"] and res[0][2] == [3, 4, 2, 5]
+    text = caplog.text
+    assert "total log probability: -3.25" in text and "normalized log probability: -0.54" in text
+    assert "total number of ended hypotheses: 1" in text and "best hypo: ab<space>c" in text
+    assert " -2.00 * 0.7 =  -1.40 for decoder" in text
