@@ -61,3 +61,39 @@ def test_collect_matches_loop(normalize_length, penalty):
             assert ("length_bonus" in h.scores) == (penalty != 0)
             if penalty != 0:
                 assert h.scores["length_bonus"] == float(step + 1)
+
+
+def test_group_bounds_partition_the_batch(monkeypatch):
+    """Utterance groups (BatchBeamSearch.n_groups) are contiguous, cover the batch once and are only used for large batches."""
+    bs = BatchBeamSearch.__new__(BatchBeamSearch)
+    monkeypatch.delenv("ESPB_SEARCH_GROUPS", raising=False)
+    bs.group_min_utts, bs.n_groups = 16, 1
+    assert bs._group_bounds(64) == [(0, 64)]
+    bs.n_groups = 2
+    assert bs._group_bounds(8) == [(0, 8)]                      # below group_min_utts
+    assert bs._group_bounds(64) == [(0, 32), (32, 64)]
+    bs.n_groups = 3
+    b = bs._group_bounds(17)
+    assert b == [(0, 6), (6, 12), (12, 17)] and all(u1 > u0 for u0, u1 in b)
+    bs.group_min_utts = 2
+    assert bs._group_bounds(5) == [(0, 5)]                      # fewer than 2 utterances per group -> no split
+    monkeypatch.setenv("ESPB_SEARCH_GROUPS", "4")
+    assert bs._group_bounds(8) == [(0, 2), (2, 4), (4, 6), (6, 8)]
+    monkeypatch.setenv("ESPB_SEARCH_GROUPS", "1")
+    assert bs._group_bounds(64) == [(0, 64)]
+
+
+def test_search_rejects_unsupported_setups():
+    import espnet_b200
+
+    dec = espnet_b200.TransformerDecoder(50, 64, attention_heads=4, linear_units=128, num_blocks=1)
+    ctc = espnet_b200.CTC(50, 64)
+    with pytest.raises(NotImplementedError):       # beam wider than one warp's selection capacity
+        BatchBeamSearch(dict(decoder=dec, ctc=ctc), dict(decoder=0.7, ctc=0.3), 33, 50, 49, 49, pre_beam_score_key="full")
+    with pytest.raises(NotImplementedError):       # joint decoding needs vocab > 1.5 * beam (pre-beam)
+        BatchBeamSearch(dict(decoder=dec, ctc=ctc), dict(decoder=0.7, ctc=0.3), 40, 50, 49, 49, pre_beam_score_key="full")
+    with pytest.raises(ValueError):                # all scorer weights zero
+        BatchBeamSearch(dict(decoder=dec, ctc=ctc), dict(decoder=0.0, ctc=0.0), 4, 50, 49, 49)
+    bs = BatchBeamSearch(dict(decoder=dec, ctc=ctc), dict(decoder=0.7, ctc=0.3, length_bonus=0.5), 4, 50, 49, 49, pre_beam_score_key="full")
+    assert bs.pre_beam_size == 6 and bs.do_pre_beam and bs.penalty == 0.5
+    assert BatchBeamSearch(dict(decoder=dec, ctc=ctc), dict(decoder=1.0, ctc=0.0), 4, 50, 49, 49).ctc is None   # zero-weight scorer dropped
