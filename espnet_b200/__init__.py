@@ -2,7 +2,8 @@
 
 Public surface mirrors the reference classes on that path:
 Speech2Text, ESPnetASRModel, DefaultFrontend, UtteranceMVN, ConformerEncoder, CTC,
-TransformerDecoder, BatchBeamSearch, Hypothesis, TooShortUttError.
+TransformerDecoder, BatchBeamSearch, Hypothesis, TooShortUttError (+ GlobalMVN, the output-side text classes, and the
+TransformerEncoder of the next scope row, whose CUDA path is still opt-in in the tests).
 All compute goes through the C-ABI CUDA library ``libespnet_b200.so`` (include/espnet_b200.h).
 """
 from .asr_inference import (ESPnetASRModel, Speech2Text, build_model, build_model_from_file, decoder_choices,  # noqa: F401
@@ -13,5 +14,7 @@ from .encoder import ConformerEncoder  # noqa: F401
 from .errors import TooShortUttError  # noqa: F401
 from .frontend import DefaultFrontend, GlobalMVN, LogMel, UtteranceMVN  # noqa: F401
 from .search import BatchBeamSearch, Hypothesis  # noqa: F401
+from .text import TokenIDConverter, build_tokenizer  # noqa: F401
+from .transformer_encoder import TransformerEncoder  # noqa: F401
 
 __version__ = "0.1.0"

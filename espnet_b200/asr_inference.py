@@ -25,13 +25,14 @@ from .errors import TooShortUttError  # noqa: F401
 from .frontend import DefaultFrontend, GlobalMVN, UtteranceMVN
 from .text import TokenIDConverter, tokenizer_for_inference
 from .search import BatchBeamSearch, Hypothesis
+from .transformer_encoder import TransformerEncoder
 
 logger = logging.getLogger(__name__)
 
 # name -> class registries, as espnet2/tasks/asr.py:95-206 (only the classes on the north-star path)
 frontend_choices = {"default": DefaultFrontend}
 normalize_choices = {"global_mvn": GlobalMVN, "utterance_mvn": UtteranceMVN}
-encoder_choices = {"conformer": ConformerEncoder}
+encoder_choices = {"conformer": ConformerEncoder, "transformer": TransformerEncoder}
 decoder_choices = {"transformer": TransformerDecoder}
 
 

@@ -300,6 +300,30 @@ __global__ void __launch_bounds__(256) relpos_softmax_smem_kernel(const float* _
   }
 }
 
+// Plain (absolute-position) attention: scores / sqrt(d_k), keys >= len masked, softmax, masked again (attention.py:121-151, 262-265).
+// One warp per (b, h, query) row, three passes over the row (the rows are short-lived L1 / L2 residents).  Output split probs [.][Tp].
+__global__ void __launch_bounds__(256) masked_softmax_kernel(const float* __restrict__ sc, int B, int H, int T, int Tp, const int* __restrict__ lens,
+                                                             float scale_div, float* __restrict__ probs, long long probs_plane) {
+  const long long rowid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (rowid >= (long long)B * H * T) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(rowid / ((long long)H * T));
+  const int len = lens[b];
+  const float* ar = sc + rowid * Tp;
+  float* pr = probs + rowid * Tp;
+  float mx = -INFINITY;
+  for (int j = lane; j < len; j += 32) mx = fmaxf(mx, ar[j] / scale_div);
+  mx = espb::warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < len; j += 32) sum += expf(ar[j] / scale_div - mx);
+  sum = espb::warp_sum(sum);
+  for (int j = lane; j < Tp; j += 32) {
+    float p = 0.f;
+    if (j < len) p = expf(ar[j] / scale_div - mx) / sum;
+    store_split(pr + j, probs_plane, p);
+  }
+}
+
 // ---------------------------------------------------------------- convolution module (convolution.py:56-79)
 // y [M][2C] = pointwise_conv1 output. GLU -> depthwise conv (K taps, zero pad at the utterance's own ends) ->
 // BatchNorm eval folded to x*bn_a + bn_b -> Swish -> split [M][C].
@@ -425,6 +449,14 @@ int espb_relpos_softmax_f32(const float* ac, const float* bd, int B, int H, int 
            (size_t)8 * Tp * sizeof(float) <= 48 * 1024 && !getenv("ESPB_SOFTMAX_3PASS"))
     relpos_softmax_smem_kernel<<<grid, 256, (size_t)8 * Tp * sizeof(float), stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
   else relpos_softmax_kernel<0><<<grid, 256, 0, stream>>>(ac, bd, B, H, T, Tp, Rp, lens, sqrt_dk, probs, probs_plane);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_masked_softmax_f32(const float* scores, int B, int H, int T, int Tp, const int* lens, float sqrt_dk, float* probs, long long probs_plane,
+                            cudaStream_t stream) {
+  const long long rows = (long long)B * H * T;
+  masked_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(scores, B, H, T, Tp, lens, sqrt_dk, probs, probs_plane);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

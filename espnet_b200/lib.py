@@ -46,6 +46,7 @@ _SIGS = {
     "espb_qu_qv_f32": [P, L, L, I, P, P, P, P, L, P],
     "espb_v_transpose_f32": [P, L, I, I, I, I, P, P, L, I, P],
     "espb_relpos_softmax_f32": [P, P, I, I, I, I, I, P, F, P, L, P],
+    "espb_masked_softmax_f32": [P, I, I, I, I, P, F, P, L, P],
     "espb_glu_dwconv_bn_swish_f32": [P, I, I, I, P, P, P, I, P, P, P, L, P],
     "espb_zero_pad_rows_f32": [P, I, I, I, P, L, I, P],
     "espb_log_softmax_rows_f32": [P, L, L, I, P],

@@ -89,6 +89,10 @@ int espb_v_transpose_f32(const float* qkv, long long qkv_plane, int B, int Tmax,
 /* rel_shift + /sqrt(d_k) + key mask + softmax (attention.py:391-414,455-457,121-151): ac [B][H][T][Tp], bd [B][H][T][Rp]. */
 int espb_relpos_softmax_f32(const float* ac, const float* bd, int B, int H, int T, int Tp, int Rp, const int* lens, float sqrt_dk,
                             float* probs, long long probs_plane, cudaStream_t stream);
+/* MultiHeadedAttention default branch (attention.py:121-151,262-265; TransformerEncoder): probs = softmax(scores / sqrt_dk) over the
+ * keys j < lens[b], 0 elsewhere; scores [B][H][T][Tp] -> probs hi/lo planes [B][H][T][Tp]. */
+int espb_masked_softmax_f32(const float* scores, int B, int H, int T, int Tp, const int* lens, float sqrt_dk, float* probs, long long probs_plane,
+                            cudaStream_t stream);
 /* GLU -> depthwise Conv1d(K, pad (K-1)/2) -> BatchNorm1d(eval, folded) -> Swish (conformer/convolution.py:56-79). */
 int espb_glu_dwconv_bn_swish_f32(const float* y, int B, int Tmax, int C, const int* lens, const float* dw_w, const float* dw_b, int K,
                                  const float* bn_a, const float* bn_b, float* out, long long out_plane, cudaStream_t stream);

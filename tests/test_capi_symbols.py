@@ -93,3 +93,21 @@ def test_unsupported_configs_are_rejected():
         espnet_b200.ConformerEncoder(80, 256, rel_pos_type="legacy", macaron_style=True)
     with pytest.raises(NotImplementedError):
         espnet_b200.DefaultFrontend(n_fft=400)
+
+
+def test_transformer_encoder_state_dict_names_match_reference_fixture():
+    """Next scope row: a reference TransformerEncoder checkpoint loads by name (strict)."""
+    import numpy as np
+    import torch
+
+    import espnet_b200
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "transformer_enc.npz"))
+    cfg = dict(zip(z["cfg_keys"].tolist(), z["cfg_vals"].tolist()))
+    w = {k[len("w:encoder."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    enc = espnet_b200.TransformerEncoder(80, output_size=cfg["d_model"], attention_heads=cfg["heads"], linear_units=cfg["ff"],
+                                         num_blocks=cfg["layers"])
+    enc.load_state_dict(w, strict=True)
+    assert espnet_b200.encoder_choices["transformer"] is espnet_b200.TransformerEncoder
+    with pytest.raises(NotImplementedError):
+        espnet_b200.TransformerEncoder(80, 64, input_layer="linear")

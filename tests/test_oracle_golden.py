@@ -88,3 +88,20 @@ def test_global_mvn_vs_reference_fixture():
         for nv in (1, 0):
             y = Fr.global_mvn(torch.from_numpy(z["x"]), torch.from_numpy(z["ilens"]), mean, std, bool(nm), bool(nv))
             np.testing.assert_array_equal(y.numpy(), z[f"y_m{nm}_v{nv}"])
+
+
+def test_transformer_encoder_oracle_vs_reference_fixture():
+    """Next scope row: the abs-pos TransformerEncoder restatement is pinned to the reference's own outputs
+    (tests/golden/transformer_enc.npz from tests/golden/make_golden_transformer.py), layer by layer."""
+    import os
+
+    from oracle import transformer_encoder as TE
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "transformer_enc.npz"))
+    cfg = dict(zip(z["cfg_keys"].tolist(), z["cfg_vals"].tolist()))
+    w = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    out, layers = TE.transformer_encode(torch.from_numpy(z["feats"]), w, cfg["heads"], cfg["layers"], return_layers=True)
+    assert out.shape[0] == int(z["olens"][0])
+    for i in range(cfg["layers"]):
+        np.testing.assert_allclose(layers[i + 1].numpy(), z[f"layer{i + 1}"], atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(out.numpy(), z["out"], atol=2e-5, rtol=1e-5)
