@@ -4,11 +4,12 @@ import torch
 
 from . import encoder as E
 from . import frontend as Fr
+from . import transformer_encoder as TE
 from .search import OracleDecoder, batch_beam_search
 
 
 class OracleSpeech2Text:
-    """cfg keys: d_model, heads, ff, enc_layers, dec_layers, vocab.  `weights` = the reference
+    """cfg keys: d_model, heads, ff, enc_layers, dec_layers, vocab (+ encoder: "conformer" | "transformer").  `weights` = the reference
     ESPnetASRModel.state_dict() (float32 CPU tensors).  blank=0, sos=eos=vocab-1
     (espnet_model.py:76-87)."""
 
@@ -33,6 +34,8 @@ class OracleSpeech2Text:
             speech = torch.tensor(speech)
         feats = Fr.log_mel(Fr.stft_power(speech.float()), self.melmat)
         feats = Fr.utterance_mvn(feats)
+        if self.cfg.get("encoder", "conformer") == "transformer":   # abs-pos TransformerEncoder (next scope row)
+            return TE.transformer_encode(feats, self.w, self.cfg["heads"], self.cfg["enc_layers"])
         return E.conformer_encode(feats, self.w, self.cfg["heads"], self.cfg["enc_layers"])
 
     @torch.no_grad()

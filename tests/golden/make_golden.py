@@ -25,6 +25,9 @@ CASES = {
                  nsamples=12000, wave_id=0),
     "small": dict(cfg=dict(d_model=96, heads=2, ff=192, enc_layers=3, dec_layers=1, vocab=97, kernel=31),
                   nsamples=20000, wave_id=3),
+    # next scope row: abs-pos TransformerEncoder + TransformerDecoder
+    "tfm": dict(cfg=dict(d_model=64, heads=4, ff=128, enc_layers=3, dec_layers=2, vocab=50), encoder="transformer",
+                nsamples=16000, wave_id=5),
 }
 DECODES = [  # (name, beam, ctc_weight, maxlenratio, minlenratio, penalty, normalize_length)
     ("joint", 4, 0.3, -8.0, 0.0, 0.0, False),
@@ -38,6 +41,9 @@ DECODES = [  # (name, beam, ctc_weight, maxlenratio, minlenratio, penalty, norma
 def run_case(name, spec):
     cfg = spec["cfg"]
     out = {"cfg_keys": np.array(list(cfg.keys())), "cfg_vals": np.array(list(cfg.values()), dtype=np.int64)}
+    if "encoder" in spec:
+        cfg = dict(cfg, encoder=spec["encoder"])
+        out["encoder_type"] = np.array(spec["encoder"])
     wave = refbuild.waveform(spec["wave_id"], spec["nsamples"])
     out["wave"] = wave.numpy()
     s2t = refbuild.build_reference(cfg, seed=0, beam_size=4, ctc_weight=0.3, maxlenratio=-8.0, nbest=10)
@@ -51,9 +57,13 @@ def run_case(name, spec):
         norm, _ = model.normalize(feats.clone(), flens)
         out["feats_norm"] = norm[0].numpy()
         layers = []
-        hooks = [model.encoder.embed.register_forward_hook(lambda m, i, o: layers.append(o[0][0][0].clone()))]
+        def first(o):   # conformer modules return ((x, pos_emb), mask), transformer modules (x, mask)
+            x = o[0]
+            return (x[0] if isinstance(x, tuple) else x)[0].clone()
+
+        hooks = [model.encoder.embed.register_forward_hook(lambda m, i, o: layers.append(first(o)))]
         for lyr in model.encoder.encoders:
-            hooks.append(lyr.register_forward_hook(lambda m, i, o: layers.append(o[0][0][0].clone())))
+            hooks.append(lyr.register_forward_hook(lambda m, i, o: layers.append(first(o))))
         enc, olens = model.encode(wave[None], lens)
         for h in hooks:
             h.remove()
@@ -82,5 +92,5 @@ def run_case(name, spec):
 
 
 if __name__ == "__main__":
-    for name, spec in CASES.items():
-        run_case(name, spec)
+    for name in (sys.argv[1:] or list(CASES)):   # optional case names: `make_golden.py tfm`
+        run_case(name, CASES[name])

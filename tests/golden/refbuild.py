@@ -50,6 +50,11 @@ def model_yaml(cfg):
         bpemodel=None,
         use_preprocessor=False,
     )
+    if cfg.get("encoder", "conformer") == "transformer":   # abs-pos TransformerEncoder (SURVEY.md 8f-1 / BASELINE configs[4])
+        y["encoder"] = "transformer"
+        y["encoder_conf"] = dict(output_size=d, attention_heads=h, linear_units=cfg["ff"], num_blocks=cfg["enc_layers"], dropout_rate=0.1,
+                                 positional_dropout_rate=0.1, attention_dropout_rate=0.0, input_layer="conv2d", normalize_before=True,
+                                 use_flash_attn=False)
     return y
 
 

@@ -11,6 +11,8 @@ DEC_NAMES = ("joint", "joint_auto", "att", "ctc", "joint_pen")
 def load(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     cfg = {k: int(v) for k, v in zip(z["cfg_keys"].tolist(), z["cfg_vals"].tolist())}
+    if "encoder_type" in z.files:
+        cfg["encoder"] = str(z["encoder_type"])
     weights = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
     return z, cfg, weights
 

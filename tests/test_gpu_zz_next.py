@@ -56,3 +56,25 @@ def test_transformer_encoder_ragged_batch_vs_oracle():
         ref = TE.transformer_encode(feats[i, :n], w, cfg["heads"], cfg["layers"])
         assert int(olens[i]) == ref.shape[0]
         assert float((out[i, : ref.shape[0]].cpu() - ref).abs().max()) < 2e-3
+
+
+def test_transformer_enc_dec_speech2text_vs_reference_fixture():
+    """Whole path with the TransformerEncoder (tests/golden/tfm.npz, made from the reference Speech2Text): encoder output, greedy ids,
+    and the n-best lists of the attention-only / joint / CTC-only decode settings."""
+    from golden_util import DEC_NAMES, decode_params, decode_results, load
+    from gpu_util import speech2text
+
+    z, cfg, w = load("tfm")
+    s2t = speech2text(cfg, w, beam_size=2, ctc_weight=0.3)
+    wave = torch.from_numpy(z["wave"])
+    speech, sl = s2t._to_batch([wave])
+    enc, _ = s2t.asr_model.encode(speech, sl)
+    assert float((enc[0].cpu() - torch.from_numpy(z["enc"])).abs().max()) < 2e-3
+    assert s2t.ctc_greedy([wave])[0] == z["ctc_greedy"].tolist()
+    for dn in DEC_NAMES:
+        res = speech2text(cfg, w, nbest=10, **decode_params(z, dn))(z["wave"])
+        gold = decode_results(z, dn)
+        assert len(res) == len(gold), dn
+        for (_, _, _, h), (yseq, score, _) in zip(res, gold):
+            assert h.yseq.tolist() == yseq, dn
+            assert abs(h.score - score) <= 2e-4 * max(1.0, abs(score))

@@ -105,3 +105,26 @@ def test_transformer_encoder_oracle_vs_reference_fixture():
     for i in range(cfg["layers"]):
         np.testing.assert_allclose(layers[i + 1].numpy(), z[f"layer{i + 1}"], atol=2e-5, rtol=1e-5)
     np.testing.assert_allclose(out.numpy(), z["out"], atol=2e-5, rtol=1e-5)
+
+
+def test_transformer_enc_dec_pipeline_vs_reference_fixture():
+    """Next scope row (BASELINE configs[4] shape family): the reference Speech2Text with a TransformerEncoder
+    (tests/golden/tfm.npz): encoder layers, CTC head and the n-best lists of all five decode settings."""
+    from oracle import transformer_encoder as TE
+
+    z, cfg, w = load("tfm")
+    assert cfg["encoder"] == "transformer"
+    enc, layers = TE.transformer_encode(torch.from_numpy(z["feats_norm"]), w, cfg["heads"], cfg["enc_layers"], return_layers=True)
+    for i, t in enumerate(layers):
+        np.testing.assert_allclose(t.numpy(), z[f"layer{i}"], atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(enc.numpy(), z["enc"], atol=2e-5, rtol=1e-5)
+    am, ids = E.ctc_greedy(enc, w)
+    assert am.tolist() == z["ctc_argmax"].tolist() and ids.tolist() == z["ctc_greedy"].tolist()
+    for dn in DEC_NAMES:
+        o = oracle.OracleSpeech2Text(cfg, w, nbest=10, **decode_params(z, dn))
+        res = o(torch.from_numpy(z["wave"]))
+        gold = decode_results(z, dn)
+        assert len(res) == len(gold), dn
+        for (_, _, _, h), (yseq, score, scores) in zip(res, gold):
+            assert h.yseq.tolist() == yseq, dn
+            assert abs(h.score - score) <= 1e-4 * max(1.0, abs(score))
