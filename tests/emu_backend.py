@@ -188,3 +188,288 @@ def install(monkeypatch):
     monkeypatch.setattr(tenc, "gemm", gemm, raising=True)
     monkeypatch.setattr(ops, "new_split", lambda *shape, device="cpu": torch.zeros((2,) + tuple(shape), dtype=torch.float32), raising=True)
     monkeypatch.setattr(enc, "new_split", ops.new_split, raising=True)
+
+
+# ------------------------------------------------------------------------------------------------ CTC head / decoder / search entry points
+# Restated with plain loops (test sizes are a few utterances x a few beam slots x tens of frames).
+LOGZERO = -10000000000.0
+
+
+def _lae(a, b):
+    m = max(a, b)
+    return m + math.log(math.exp(a - m) + math.exp(b - m))
+
+
+def _step(step_ptr):
+    return int(step_ptr.view(-1)[0]) if step_ptr is not None else 0
+
+
+def _log_softmax_rows(x, rows, ld, V):
+    xv = torch.as_strided(x, (rows, V), (ld, 1), x.storage_offset())
+    xv.copy_(torch.log_softmax(xv, dim=-1))
+
+
+def _argmax_rows(x, rows, ld, V, out):
+    xv = torch.as_strided(x, (rows, V), (ld, 1), x.storage_offset())
+    _flat(out)[:rows] = torch.argmax(xv, dim=-1).to(torch.int32)
+
+
+def _ctc_collapse(am, B, Tmax, lens, blank, out_ids, out_len):
+    a, o = am.view(B, Tmax), out_ids.view(B, Tmax)
+    for b in range(B):
+        n = 0
+        for t in range(int(lens[b])):
+            v = int(a[b, t])
+            if v != blank and (t == 0 or int(a[b, t - 1]) != v):
+                o[b, n] = v
+                n += 1
+        out_len.view(-1)[b] = n
+
+
+def _rows_topk(x, rows, ld, V, scale, k, ids, vals):
+    xv = torch.as_strided(x, (rows, V), (ld, 1), x.storage_offset()) * scale
+    for r in range(rows):
+        v = xv[r].clone()
+        for j in range(k):                      # descending, ties -> lower index
+            i = int(torch.argmax(v))            # torch.argmax returns the first maximum
+            ids.view(-1)[r * k + j] = i
+            vals.view(-1)[r * k + j] = v[i]
+            v[i] = float("-inf")
+
+
+def _dec_embed(last_tok, emb, pe, pos, step_ptr, n, D, scale, x):
+    p = pos + _step(step_ptr)
+    x.view(n, D).copy_(emb[last_tok.view(-1)[:n].long()] * scale + pe[p])
+
+
+def _dec_self_attn(qkv, kc, vc, anc, anc_ld, n, D, H, pos, step_ptr, max_pos, ctx, ctx_plane):
+    pos = pos + _step(step_ptr)
+    dk = D // H
+    q3 = qkv.view(n, 3 * D)
+    kc[pos].view(n, D).copy_(q3[:, D:2 * D])
+    vc[pos].view(n, D).copy_(q3[:, 2 * D:])
+    an = anc.view(n, anc_ld)
+    out = torch.zeros(n, D)
+    for s in range(n):
+        rows = [int(an[s, j]) for j in range(pos)] + [s]
+        K = torch.stack([kc[j].view(n, D)[rows[j]] for j in range(pos + 1)])     # [pos+1][D]
+        Vv = torch.stack([vc[j].view(n, D)[rows[j]] for j in range(pos + 1)])
+        for h in range(H):
+            sl = slice(h * dk, (h + 1) * dk)
+            sc = (K[:, sl] @ q3[s, sl]) / math.sqrt(dk)
+            out[s, sl] = torch.softmax(sc, dim=0) @ Vv[:, sl]
+    _store(_flat(ctx), torch.arange(n * D), out.view(-1), True, ctx_plane)
+
+
+def _dec_src_attn(q, kmem, vmem, U, Tmax, lens, W, D, H, ctx, ctx_plane):
+    dk = D // H
+    qv, km, vm = q.view(U * W, D), kmem.view(U, H, Tmax, dk), vmem.view(U, H, Tmax, dk)
+    out = torch.zeros(U * W, D)
+    for u in range(U):
+        T = int(lens[u])
+        for h in range(H):
+            sl = slice(h * dk, (h + 1) * dk)
+            sc = (qv[u * W:(u + 1) * W, sl] @ km[u, h, :T].t()) / math.sqrt(dk)      # no memory mask beyond the utterance's own frames
+            out[u * W:(u + 1) * W, sl] = torch.softmax(sc, dim=-1) @ vm[u, h, :T]
+    _store(_flat(ctx), torch.arange(U * W * D), out.view(-1), True, ctx_plane)
+
+
+def _x(logp, u, Tmax, V, token_major):
+    """Returns f(t, c) reading the posterior of utterance u in either layout."""
+    base = logp.view(-1)[u * Tmax * V:(u + 1) * Tmax * V]
+    return (lambda t, c: float(base[c * Tmax + t])) if token_major else (lambda t, c: float(base[t * V + c]))
+
+
+def _ctc_init_state(logp, U, Tmax, V, lens, blank, W, r, s_prev):
+    rr = r.view(U * W, Tmax, 4)
+    for s in range(U * W):
+        u = s // W
+        x, T, c = _x(logp, u, Tmax, V, 0), int(lens[u]), 0.0
+        for t in range(Tmax):
+            if t < T:
+                c = float(torch.tensor(c, dtype=torch.float32) + torch.tensor(x(t, blank), dtype=torch.float32))
+            rb = c if t < T else LOGZERO
+            rr[s, t] = torch.tensor([LOGZERO, rb, _lae(LOGZERO, rb), 0.0])
+        s_prev.view(-1)[s] = 0.0
+
+
+def _transpose_tv(x, U, Tmax, V, xt):
+    xt.view(U, V, Tmax).copy_(x.view(U, Tmax, V).transpose(1, 2))
+
+
+def _log_psi(x, T, blank, eos, rp, c, last, out_len):
+    if c == eos:
+        return float(rp[T - 1, 2])
+    if c == blank:
+        return LOGZERO
+    start = max(out_len, 1)
+    terms = [(float(rp[t - 1, 1]) if c == last else float(rp[t - 1, 2])) + x(t, c) for t in range(start, T)]
+    terms.append(x(0, c) if out_len == 0 else LOGZERO)
+    return float(torch.logsumexp(torch.tensor(terms, dtype=torch.float64), dim=0))
+
+
+def _ctc_score_cands(logp, U, Tmax, V, lens, blank, eos, W, r_prev, s_prev, last_tok, out_len, step_ptr, cand, P, part, psi, valid, token_major):
+    out_len += _step(step_ptr)
+    rp, cd = r_prev.view(U * W, Tmax, 4), cand.view(U * W, P)
+    for s in range(U * W):
+        u = s // W
+        x = _x(logp, u, Tmax, V, token_major)
+        for j in range(P + 1):
+            c = int(cd[s, j]) if j < P else eos
+            ok = 0 if (j == P and bool((cd[s] == eos).any())) else 1
+            v = _log_psi(x, int(lens[u]), blank, eos, rp[s], c, int(last_tok.view(-1)[s]), out_len)
+            i = s * (P + 1) + j
+            psi.view(-1)[i], part.view(-1)[i], valid.view(-1)[i] = v, v - float(s_prev.view(-1)[s]), ok
+
+
+def _ctc_score_dense(logp, U, Tmax, V, lens, blank, eos, W, r_prev, s_prev, last_tok, out_len, part):
+    rp = r_prev.view(U * W, Tmax, 4)
+    for s in range(U * W):
+        u = s // W
+        x = _x(logp, u, Tmax, V, 0)
+        for c in range(V):
+            part.view(-1)[s * V + c] = _log_psi(x, int(lens[u]), blank, eos, rp[s], c, int(last_tok.view(-1)[s]), out_len) - float(s_prev.view(-1)[s])
+
+
+def _ctc_advance(logp, U, Tmax, V, lens, blank, eos, W, r_prev, parent, par_last_tok, new_tok, new_active, out_len, step_ptr, r_new, s_new,
+                 token_major):
+    out_len += _step(step_ptr)
+    rp, ro = r_prev.view(U * W, Tmax, 4), r_new.view(U * W, Tmax, 4)
+    Z4 = torch.tensor([LOGZERO, LOGZERO, _lae(LOGZERO, LOGZERO), 0.0])
+    for s in range(U * W):
+        u, c, act = s // W, int(new_tok.view(-1)[s]), int(new_active.view(-1)[s])
+        if not act or c == eos or c == blank:
+            ro[s] = Z4
+            s_new.view(-1)[s] = LOGZERO if (act and c == blank) else 0.0
+            continue
+        p, T = int(parent.view(-1)[s]), int(lens[u])
+        x, last = _x(logp, u, Tmax, V, token_major), int(par_last_tok.view(-1)[p])
+        start = max(out_len, 1)
+        rn, rb = (x(0, c) if out_len == 0 else LOGZERO), LOGZERO
+        ro[s] = Z4
+        ro[s, start - 1] = torch.tensor([rn, rb, _lae(rn, rb), 0.0])
+        for t in range(start, T):
+            phi = float(rp[p, t - 1, 1]) if c == last else float(rp[p, t - 1, 2])
+            rn, rb = _lae(rn, phi) + x(t, c), _lae(rn, rb) + x(t, blank)
+            ro[s, t] = torch.tensor([rn, rb, _lae(rn, rb), 0.0])
+        s_new.view(-1)[s] = _log_psi(x, T, blank, eos, rp[p], c, last, out_len)
+
+
+def _beam_select(score, sc_dec, sc_ctc, active, n_score, n_sc_dec, n_sc_ctc, n_active, n_last_tok, n_parent, bp_parent, bp_token, e_count,
+                 e_step, e_slot, e_score, e_dec, e_ctc, ended_cap, best_at, best_all, utt_done, U, W, P, V, step, step_ptr, maxlen, minlen, eos,
+                 w_dec, w_ctc, penalty, mode, cand_ids, cand_val, logp_dec, part, valid, end_detect, maxlen_cap):
+    step += _step(step_ptr)
+    f32 = lambda v: float(torch.tensor(v, dtype=torch.float32))  # noqa: E731
+    PC = P + 1 if mode == 1 else P
+    fl = lambda t: t.view(-1)  # noqa: E731
+    for u in range(U):
+        done = int(fl(utt_done)[u]) != 0
+        tot = []
+        for ci in range(W * PC):
+            w, j = divmod(ci, PC)
+            s, t = u * W + w, float("-inf")
+            if not done and int(fl(active)[s]):
+                if mode == 1:
+                    if int(fl(valid)[s * PC + j]):
+                        dec = float(fl(cand_val)[s * P + j]) if j < P else f32(w_dec * float(fl(logp_dec)[s * V + eos]))
+                        t = f32(f32(f32(dec + penalty) + f32(w_ctc * float(fl(part)[s * PC + j]))) + float(fl(score)[s]))
+                else:
+                    t = f32(f32(float(fl(cand_val)[s * P + j]) + penalty) + float(fl(score)[s]))
+            tot.append(t)
+        mlen = int(fl(maxlen)[u])
+        last_step, step_best = step == mlen - 1, float("-inf")
+        for k in range(W):
+            ns = u * W + k
+            bp = step * U * W + ns
+            best = max(tot) if tot else float("-inf")
+            if best == float("-inf"):
+                fl(n_active)[ns], fl(n_score)[ns], fl(n_sc_dec)[ns], fl(n_sc_ctc)[ns], fl(n_last_tok)[ns] = 0, 0.0, 0.0, 0.0, eos
+                fl(n_parent)[ns], fl(bp_parent)[bp], fl(bp_token)[bp] = ns, -1, eos
+                continue
+            bidx = tot.index(best)               # ties -> lower flat index
+            tot[bidx] = float("-inf")
+            w, j = divmod(bidx, PC)
+            s = u * W + w
+            tok = eos if (mode == 1 and j == P) else int(fl(cand_ids)[s * P + j])
+            dlogp = float(fl(logp_dec)[s * V + tok]) if mode != 2 else 0.0
+            cpart = float(fl(part)[s * PC + j]) if mode == 1 else (float(fl(part)[s * V + tok]) if mode == 2 else 0.0)
+            ndec, nctc = f32(float(fl(sc_dec)[s]) + dlogp), f32(float(fl(sc_ctc)[s]) + cpart)
+            fl(bp_parent)[bp], fl(bp_token)[bp], fl(n_parent)[ns] = s, tok, s
+            fl(n_score)[ns], fl(n_sc_dec)[ns], fl(n_sc_ctc)[ns], fl(n_last_tok)[ns] = best, ndec, nctc, tok
+            ended = last_step or tok == eos
+            fl(n_active)[ns] = 0 if ended else 1
+            if ended and step >= int(fl(minlen)[u]):
+                e = int(fl(e_count)[u])
+                if e < ended_cap:
+                    o = u * ended_cap + e
+                    fl(e_step)[o], fl(e_slot)[o], fl(e_score)[o], fl(e_dec)[o], fl(e_ctc)[o] = step, ns, best, ndec, nctc
+                    fl(e_count)[u] = e + 1
+                step_best = max(step_best, best)
+        if not done:
+            if end_detect:
+                if step < maxlen_cap:
+                    fl(best_at)[u * maxlen_cap + step] = step_best
+                ball = max(float(fl(best_all)[u]), step_best)
+                fl(best_all)[u] = ball
+                count = 0
+                for m in range(3):
+                    j = step - m - 2
+                    if 0 <= j < maxlen_cap:
+                        b = float(fl(best_at)[u * maxlen_cap + j])
+                        if b > float("-inf") and b - ball < -10.0:
+                            count += 1
+                if count == 3:
+                    fl(utt_done)[u] = 1
+            if last_step:
+                fl(utt_done)[u] = 1
+
+
+def _anc_update(anc, n_anc, anc_ld, parent, pos, step_ptr, n):
+    pos += _step(step_ptr)
+    a, na = anc.view(n, anc_ld), n_anc.view(n, anc_ld)
+    for s in range(n):
+        p = int(parent.view(-1)[s])
+        na[s, :pos] = a[p, :pos]
+        na[s, pos] = p
+
+
+def _step_inc(step):
+    step.view(-1)[0] += 1
+
+
+def _count_active(active, n, out):
+    out.view(-1)[0] = int((active.view(-1)[:n] != 0).sum())
+
+
+_TABLE.update({"espb_log_softmax_rows_f32": _log_softmax_rows, "espb_argmax_rows_f32": _argmax_rows, "espb_ctc_collapse_i32": _ctc_collapse,
+               "espb_rows_topk_f32": _rows_topk, "espb_dec_embed_f32": _dec_embed, "espb_dec_self_attn_f32": _dec_self_attn,
+               "espb_dec_src_attn_f32": _dec_src_attn, "espb_ctc_init_state_f32": _ctc_init_state, "espb_transpose_tv_f32": _transpose_tv,
+               "espb_ctc_score_cands_f32": _ctc_score_cands, "espb_ctc_score_dense_f32": _ctc_score_dense, "espb_ctc_advance_f32": _ctc_advance,
+               "espb_beam_select": _beam_select, "espb_anc_update_i32": _anc_update, "espb_step_inc_i32": _step_inc,
+               "espb_count_active_i32": _count_active})
+
+
+def install_search(monkeypatch):
+    """install() + the CTC head, decoder and search modules; CUDA streams / graphs are taken out of the picture (host logic only)."""
+    import contextlib
+
+    import espnet_b200.ctc as ctc
+    import espnet_b200.decoder as dec
+    import espnet_b200.search as search
+
+    install(monkeypatch)
+    for mod in (ctc, dec, search):
+        monkeypatch.setattr(mod, "call", call, raising=True)
+        monkeypatch.setattr(mod, "ptr", ptr, raising=True)
+    class NoStream:   # stands in for torch.cuda.Stream: ordering is trivially sequential on the host
+        def wait_stream(self, other):
+            pass
+
+        def wait_event(self, ev):
+            pass
+
+    monkeypatch.setattr(search.BatchBeamSearch, "use_cuda_graphs", False, raising=True)
+    monkeypatch.setattr(search.BatchBeamSearch, "_side_stream", lambda self, dev, g=0: None, raising=True)
+    monkeypatch.setattr(search.BatchBeamSearch, "_group_stream", lambda self, dev, g: NoStream(), raising=True)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: NoStream(), raising=True)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext(), raising=True)

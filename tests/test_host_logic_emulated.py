@@ -93,3 +93,95 @@ def test_transformer_encoder_ragged_batch_host_logic(monkeypatch):
         ref = TE.transformer_encode(feats[i, :n], w, cfg["heads"], cfg["enc_layers"])
         assert int(olens[i]) == ref.shape[0]
         np.testing.assert_allclose(out[i, : ref.shape[0]].numpy(), ref.numpy(), atol=5e-5, rtol=1e-5)
+
+
+def _search_setup(case, dn):
+    """The scorer / weight wiring of Speech2Text.__init__ (asr_inference.py:310-381) around a CPU-built model."""
+    import argparse
+
+    import espnet_b200
+    from espnet_b200.search import BatchBeamSearch
+    from gpu_util import refbuild   # model_yaml only (does not import the reference)
+    from golden_util import decode_params
+
+    z, cfg, w = load(case)
+    model = espnet_b200.build_model(argparse.Namespace(**refbuild.model_yaml(cfg)))
+    model.load_state_dict(w, strict=True)
+    model.eval()
+    kw = decode_params(z, dn)
+    cw = kw["ctc_weight"]
+    scorers = dict(decoder=model.decoder if cw != 1.0 else None, ctc=model.ctc)
+    weights = dict(decoder=1.0 - cw, ctc=cw, lm=1.0, ngram=0.9, length_bonus=kw["penalty"])
+    bs = BatchBeamSearch(scorers, weights, kw["beam_size"], len(model.token_list), model.sos, model.eos, token_list=model.token_list,
+                         pre_beam_score_key=None if cw == 1.0 else "full", normalize_length=kw["normalize_length"])
+    return z, model, bs, kw
+
+
+@pytest.mark.parametrize("case,dn", [("tiny", "joint"), ("tiny", "att"), ("tiny", "ctc"), ("tiny", "joint_pen"), ("tiny", "joint_auto"),
+                                     ("tfm", "att"), ("tfm", "joint")])
+def test_search_and_decoder_host_logic_vs_reference_fixture(case, dn, monkeypatch):
+    """Encoder -> CTC head -> decoder memory / incremental decoder -> device-resident beam search, all host code of the product with the
+    kernels emulated on CPU: n-best lists of the reference fixtures (attention-only, joint, CTC-only, penalty / minlen /
+    normalize_length, end detection)."""
+    from golden_util import decode_results
+
+    emu_backend.install_search(monkeypatch)
+    z, model, bs, kw = _search_setup(case, dn)
+    feats = torch.from_numpy(z["feats_norm"])[None]
+    enc, enc_lens, _ = model.encoder(feats, torch.tensor([feats.shape[1]]))
+    hyps = bs.forward_batch(enc, enc_lens, model.enc_split(enc), kw["maxlenratio"], kw["minlenratio"])[0]
+    gold = decode_results(z, dn)
+    got = hyps[:10]
+    assert len(got) == len(gold)
+    for h, (yseq, score, scores) in zip(got, gold):
+        assert h.yseq.tolist() == yseq
+        assert abs(h.score - score) <= 2e-4 * max(1.0, abs(score))
+    assert "espb_beam_select" in emu_backend.calls
+    assert ("espb_anc_update_i32" in emu_backend.calls) == (dn != "ctc")          # the ancestor table belongs to the decoder cache
+    assert ("espb_transpose_tv_f32" in emu_backend.calls) == (dn not in ("att", "ctc"))   # token-major posteriors: joint mode only
+
+
+def test_ctc_greedy_host_logic_vs_reference_fixture(monkeypatch):
+    emu_backend.install_search(monkeypatch)
+    z, model, bs, kw = _search_setup("small", "joint")
+    feats = torch.from_numpy(z["feats_norm"])[None]
+    enc, enc_lens, _ = model.encoder(feats, torch.tensor([feats.shape[1]]))
+    ids, cnt, am = model.ctc.greedy(enc, enc_lens, model.enc_split(enc), blank=model.blank_id)
+    assert am[0, : int(enc_lens[0])].tolist() == z["ctc_argmax"].tolist()
+    assert ids[0, : int(cnt[0])].tolist() == z["ctc_greedy"].tolist()
+
+
+def test_ragged_batch_and_utterance_groups_host_logic(monkeypatch):
+    """A ragged batch searched (a) as one group and (b) as two groups on separate (here: stand-in) streams gives, per utterance, the
+    oracle's batch-1 n-best list."""
+    import oracle
+
+    emu_backend.install_search(monkeypatch)
+    z, model, bs, kw = _search_setup("tiny", "joint")
+    cfgz, cfg, w = load("tiny")
+    g = torch.Generator().manual_seed(4)
+    lens = [90, 61, 75]
+    feats = torch.zeros(3, 90, 80)
+    for i, n in enumerate(lens):
+        feats[i, :n] = torch.randn(n, 80, generator=g)
+    enc, enc_lens, _ = model.encoder(feats, torch.tensor(lens))
+    single = bs.forward_batch(enc, enc_lens, model.enc_split(enc), -6.0, 0.0)
+    bs.group_min_utts, bs.n_groups = 2, 2
+    assert bs._group_bounds(3) == [(0, 3)] and bs._group_bounds(4) == [(0, 2), (2, 4)]
+    enc4 = torch.cat([enc, enc[:1]], 0).contiguous()          # 4 utterances -> two groups of two
+    lens4 = torch.cat([enc_lens, enc_lens[:1]])
+    grouped = bs.forward_batch(enc4, lens4, None, -6.0, 0.0)
+    o = oracle.OracleSpeech2Text(cfg, w, beam_size=kw["beam_size"], ctc_weight=kw["ctc_weight"], maxlenratio=-6.0, nbest=10)
+    for i, n in enumerate(lens):
+        from oracle import encoder as OE
+        from oracle.search import batch_beam_search
+
+        ref_enc = OE.conformer_encode(feats[i, :n], w, cfg["heads"], cfg["enc_layers"])
+        logp = torch.log_softmax(OE.ctc_logits(ref_enc, o.w), dim=-1)
+        ref = batch_beam_search(ref_enc, o.decoder, logp, beam_size=o.beam_size, ctc_weight=o.ctc_weight, vocab=o.vocab, sos=o.sos, eos=o.eos,
+                                maxlenratio=-6.0, minlenratio=0.0, penalty=0.0, normalize_length=False)
+        for res in (single[i], grouped[i]):
+            assert [h.yseq.tolist() for h in res] == [h.yseq.tolist() for h in ref]
+            for a, b in zip(res, ref):
+                assert abs(a.score - float(b.score)) <= 2e-4 * max(1.0, abs(float(b.score)))
+    assert [h.yseq.tolist() for h in grouped[3]] == [h.yseq.tolist() for h in grouped[0]]
