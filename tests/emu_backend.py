@@ -473,3 +473,62 @@ def install_search(monkeypatch):
     monkeypatch.setattr(search.BatchBeamSearch, "_group_stream", lambda self, dev, g: NoStream(), raising=True)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: NoStream(), raising=True)
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext(), raising=True)
+
+
+# ------------------------------------------------------------------------------------------------ frontend / normalisation entry points
+def _stft_logmel(wave, lens, B, L, window, tw, start, count, offset, weight, n_mels, out, Tf, partial):
+    """frontend.cu: torch.stft semantics per utterance (own reflect padding), power, SPARSE mel filterbank exactly as the tables describe it,
+    clamp 1e-10, log; frames >= 1 + len/128 are zero.  The per-block column sums go to block 0 (only their total is contractual)."""
+    o = out.view(B, Tf, n_mels)
+    o.zero_()
+    if partial is not None:
+        partial.zero_()
+    for b in range(B):
+        n = int(lens[b])
+        spec = torch.stft(wave.view(B, L)[b, :n], 512, hop_length=128, win_length=512, window=window, center=True, pad_mode="reflect",
+                          normalized=False, onesided=True, return_complex=True)
+        power = (spec.real ** 2 + spec.imag ** 2).t()          # [Tf_b][257]
+        tf_b = 1 + n // 128
+        assert power.shape[0] == tf_b
+        for j in range(n_mels):
+            s, c, w0 = int(start[j]), int(count[j]), int(offset[j])
+            mel = (power[:, s:s + c] * weight[w0:w0 + c]).sum(-1) if c > 0 else torch.zeros(tf_b)
+            o[b, :tf_b, j] = torch.log(torch.clamp(mel, min=1e-10))
+        if partial is not None:
+            partial.view(B, -1, n_mels)[b, 0] = o[b, :tf_b].sum(0)
+
+
+def _utt_mvn_from_partial(feats, wave_lens, B, Tf_max, n_mels, partial):
+    f = feats.view(B, Tf_max, n_mels)
+    for b in range(B):
+        tf_b = 1 + int(wave_lens[b]) // 128
+        f[b, :tf_b] -= partial.view(B, -1, n_mels)[b].sum(0) / tf_b
+
+
+def _utt_mvn(feats, feat_lens, B, Tf_max, n_mels, ws):
+    f = feats.view(B, Tf_max, n_mels)
+    for b in range(B):
+        n = int(feat_lens[b])
+        f[b, :n] -= f[b, :n].sum(0) / n
+
+
+def _global_mvn(feats, feat_lens, B, Tmax, D, mean, std, norm_means, norm_vars):
+    f = feats.view(B, Tmax, D)
+    for b in range(B):
+        n = int(feat_lens[b])
+        if norm_means:
+            f[b] -= mean
+        f[b, n:] = 0.0
+        if norm_vars:
+            f[b] /= std
+
+
+_TABLE.update({"espb_stft_logmel_f32": _stft_logmel, "espb_utt_mvn_from_partial_f32": _utt_mvn_from_partial, "espb_utt_mvn_f32": _utt_mvn,
+               "espb_global_mvn_f32": _global_mvn})
+
+
+def install_frontend(monkeypatch):
+    import espnet_b200.frontend as fe
+
+    monkeypatch.setattr(fe, "call", call, raising=True)
+    monkeypatch.setattr(fe, "ptr", ptr, raising=True)

@@ -185,3 +185,53 @@ def test_ragged_batch_and_utterance_groups_host_logic(monkeypatch):
             for a, b in zip(res, ref):
                 assert abs(a.score - float(b.score)) <= 2e-4 * max(1.0, abs(float(b.score)))
     assert [h.yseq.tolist() for h in grouped[3]] == [h.yseq.tolist() for h in grouped[0]]
+
+
+@pytest.mark.parametrize("case", ["tiny", "small"])
+def test_frontend_host_logic_vs_reference_fixture(case, monkeypatch):
+    """DefaultFrontend's host side (sparse mel tables built from the melmat buffer, window, frame counts) and UtteranceMVN (fused partial-sum
+    path and standalone path) against the reference's features."""
+    import espnet_b200
+
+    emu_backend.install_frontend(monkeypatch)
+    z, cfg, w = load(case)
+    fe = espnet_b200.DefaultFrontend()
+    fe.load_state_dict({"logmel.melmat": w["frontend.logmel.melmat"]}, strict=True)
+    wave = torch.from_numpy(z["wave"])
+    feats, flens = fe(wave[None], torch.tensor([wave.numel()]))
+    assert int(flens[0]) == z["feats"].shape[0] == feats.shape[1]
+    np.testing.assert_allclose(feats[0].numpy(), z["feats"], atol=2e-4, rtol=1e-5)
+    norm, _ = espnet_b200.UtteranceMVN()(feats, flens)                       # consumes the stashed partial sums, in place
+    assert norm.data_ptr() == feats.data_ptr()
+    np.testing.assert_allclose(norm[0].numpy(), z["feats_norm"], atol=2e-4, rtol=1e-5)
+    alone, _ = espnet_b200.UtteranceMVN()(torch.from_numpy(z["feats"])[None].clone(), flens)   # no stash: standalone kernels
+    np.testing.assert_allclose(alone[0].numpy(), z["feats_norm"], atol=2e-4, rtol=1e-5)
+
+
+def test_frontend_ragged_and_global_mvn_host_logic(monkeypatch, tmp_path):
+    import espnet_b200
+    from oracle import frontend as OF
+
+    emu_backend.install_frontend(monkeypatch)
+    fe = espnet_b200.DefaultFrontend()
+    g = torch.Generator().manual_seed(9)
+    lens = [9000, 4000, 6789]
+    wave = torch.zeros(3, 9000)
+    for i, n in enumerate(lens):
+        wave[i, :n] = 0.1 * torch.randn(n, generator=g)
+    feats, flens = fe(wave, torch.tensor(lens))
+    for i, n in enumerate(lens):
+        ref = OF.frontend_forward(wave[i, :n], fe.logmel.melmat)
+        assert int(flens[i]) == ref.shape[0]
+        np.testing.assert_allclose(feats[i, : ref.shape[0]].numpy(), ref.numpy(), atol=2e-4, rtol=1e-5)
+        assert float(feats[i, ref.shape[0]:].abs().max() if ref.shape[0] < feats.shape[1] else 0.0) == 0.0
+    zg = np.load(__import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "gmvn.npz"))
+    f = tmp_path / "stats.npz"
+    np.savez(f, count=zg["stats_count"], sum=zg["stats_sum"], sum_square=zg["stats_sum_square"])
+    for nm in (1, 0):
+        for nv in (1, 0):
+            m = espnet_b200.GlobalMVN(str(f), norm_means=bool(nm), norm_vars=bool(nv))
+            y, _ = m(torch.from_numpy(zg["x"]).clone(), torch.from_numpy(zg["ilens"]))
+            np.testing.assert_array_equal(y.numpy(), zg[f"y_m{nm}_v{nv}"])
+    with pytest.raises(RuntimeError):
+        fe(torch.zeros(1, 200), torch.tensor([200]))          # shorter than n_fft/2: reflect padding impossible (torch.stft raises too)
