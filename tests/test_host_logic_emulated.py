@@ -235,3 +235,23 @@ def test_frontend_ragged_and_global_mvn_host_logic(monkeypatch, tmp_path):
             np.testing.assert_array_equal(y.numpy(), zg[f"y_m{nm}_v{nv}"])
     with pytest.raises(RuntimeError):
         fe(torch.zeros(1, 200), torch.tensor([200]))          # shorter than n_fft/2: reflect padding impossible (torch.stft raises too)
+
+
+@pytest.mark.parametrize("case,dn", [("tiny", "joint"), ("small", "joint_pen"), ("tfm", "att")])
+def test_waveform_to_nbest_host_logic(case, dn, monkeypatch):
+    """The whole path from the waveform: ESPnetASRModel.encode (frontend -> normalize -> encoder) and the search, every kernel emulated,
+    against the reference Speech2Text's n-best list for the same waveform."""
+    from golden_util import decode_results
+
+    emu_backend.install_search(monkeypatch)
+    emu_backend.install_frontend(monkeypatch)
+    z, model, bs, kw = _search_setup(case, dn)
+    wave = torch.from_numpy(z["wave"])
+    enc, enc_lens = model.encode(wave[None], torch.tensor([wave.numel()]))
+    np.testing.assert_allclose(enc[0].numpy(), z["enc"], atol=3e-4, rtol=1e-4)
+    hyps = bs.forward_batch(enc, enc_lens, model.enc_split(enc), kw["maxlenratio"], kw["minlenratio"])[0][:10]
+    gold = decode_results(z, dn)
+    assert len(hyps) == len(gold)
+    for h, (yseq, score, _) in zip(hyps, gold):
+        assert h.yseq.tolist() == yseq
+        assert abs(h.score - score) <= 3e-4 * max(1.0, abs(score))
