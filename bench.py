@@ -392,7 +392,7 @@ def run_b200(args, rank, local_rank, world):
                      "note": "algorithmic FLOPs (2MNK); each is executed as 3 tf32 MMAs at half the bf16 rate, so 1/6 of the bf16 peak is the ceiling of this formulation"},
     }
     print("[bench] gpu arm done: " + json.dumps(line), file=sys.stderr, flush=True)
-    if args.cpu_baseline:
+    if args.cpu_baseline and world == 1:   # the host-core baseline is reported by the single-GPU run only
         cpu_threads(cfg)
         est, desc, _ = cpu_sample_seconds(cfg, secs, beam, ctcw, mlr, host[0])
         line["cpu_baseline"] = {"value": 1.0 / est, "unit": "utterances/s", "cores": torch.get_num_threads(), "kind": "port",
