@@ -145,7 +145,7 @@ def _end_detect(ended: List[Hyp], i, M=3, D_end=math.log(1 * math.exp(-10))):
 
 
 def batch_beam_search(enc, decoder, ctc_logp, *, beam_size, ctc_weight, vocab, sos, eos, blank=0,
-                      maxlenratio=0.0, minlenratio=0.0, penalty=0.0, normalize_length=False, trace=None):
+                      maxlenratio=0.0, minlenratio=0.0, penalty=0.0, normalize_length=False, trace=None, lm=None, lm_weight=0.0):
     """BeamSearch.forward + BatchBeamSearch.search/post_process for one utterance
     (beam_search.py:385-498; batch_beam_search.py:253-357, 359-423).  Scorers as Speech2Text wires
     them (asr_inference.py:168-176, 310-316): decoder weight 1-ctc_weight, ctc weight ctc_weight,
@@ -155,8 +155,9 @@ def batch_beam_search(enc, decoder, ctc_logp, *, beam_size, ctc_weight, vocab, s
     w_dec, w_ctc = 1.0 - ctc_weight, ctc_weight
     use_dec = w_dec != 0 and decoder is not None
     use_ctc = w_ctc != 0
+    use_lm = lm is not None and lm_weight != 0   # asr_inference.py:178-191: scorers["lm"] = lm.lm, a full scorer with weight lm_weight
     pre_beam = int(1.5 * beam_size)
-    do_pre_beam = use_ctc and use_dec and pre_beam < vocab  # pre_beam_score_key "full" unless ctc_weight==1
+    do_pre_beam = use_ctc and (use_dec or use_lm) and ctc_weight != 1.0 and pre_beam < vocab  # pre_beam_score_key "full" unless ctc_weight==1
     if maxlenratio == 0:
         maxlen = T
     elif maxlenratio < 0:
@@ -168,7 +169,7 @@ def batch_beam_search(enc, decoder, ctc_logp, *, beam_size, ctc_weight, vocab, s
 
     yseq = torch.full((1, 1), sos, dtype=torch.long)
     score = torch.zeros(1)
-    sc_dec, sc_ctc, sc_lb = torch.zeros(1), torch.zeros(1), torch.zeros(1)
+    sc_dec, sc_ctc, sc_lb, sc_lm = torch.zeros(1), torch.zeros(1), torch.zeros(1), torch.zeros(1)
     cache, r_state, s_state = None, None, None
     ended: List[Hyp] = []
     for i in range(maxlen):
@@ -179,6 +180,9 @@ def batch_beam_search(enc, decoder, ctc_logp, *, beam_size, ctc_weight, vocab, s
             weighted += w_dec * logp
         if penalty != 0:
             weighted += penalty * 1.0
+        if use_lm:
+            lm_logp = lm.batch_score(yseq)
+            weighted += lm_weight * lm_logp
         part_ids = torch.topk(weighted, pre_beam, dim=-1)[1] if do_pre_beam else None
         if use_ctc:
             part, r_new, log_psi, idmap = scorer.score(yseq, r_state, s_state, part_ids)
@@ -199,6 +203,8 @@ def batch_beam_search(enc, decoder, ctc_logp, *, beam_size, ctc_weight, vocab, s
             cache = [c[prev] for c in new_cache]
         if penalty != 0:
             sc_lb = sc_lb[prev] + 1.0
+        if use_lm:
+            sc_lm = sc_lm[prev] + lm_logp[prev, tok]
         if use_ctc:
             sc_ctc = sc_ctc[prev] + part[prev, tok]
             col = idmap[prev, tok] if idmap is not None else tok  # select_state, scorers/ctc.py:40-63
@@ -217,11 +223,14 @@ def batch_beam_search(enc, decoder, ctc_logp, *, beam_size, ctc_weight, vocab, s
                     scores["ctc"] = float(sc_ctc[b])
                 if penalty != 0:
                     scores["length_bonus"] = float(sc_lb[b])
+                if use_lm:
+                    scores["lm"] = float(sc_lm[b])
                 ended.append(Hyp(yseq=yseq[b].clone(), score=float(score[b]), scores=scores))
         keep = torch.nonzero(~is_eos).view(-1)
         yseq, score = yseq[keep], score[keep]
         sc_dec, sc_ctc, sc_lb = sc_dec[keep] if use_dec else sc_dec, sc_ctc[keep] if use_ctc else sc_ctc, \
             sc_lb[keep] if penalty != 0 else sc_lb
+        sc_lm = sc_lm[keep] if use_lm else sc_lm
         if use_dec:
             cache = [c[keep] for c in cache]
         if use_ctc:
@@ -236,5 +245,5 @@ def batch_beam_search(enc, decoder, ctc_logp, *, beam_size, ctc_weight, vocab, s
         return batch_beam_search(enc, decoder, ctc_logp, beam_size=beam_size, ctc_weight=ctc_weight, vocab=vocab,
                                  sos=sos, eos=eos, blank=blank, maxlenratio=maxlenratio,
                                  minlenratio=max(0.0, minlenratio - 0.1), penalty=penalty,
-                                 normalize_length=normalize_length)
+                                 normalize_length=normalize_length, lm=lm, lm_weight=lm_weight)
     return nbest

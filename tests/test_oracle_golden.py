@@ -128,3 +128,36 @@ def test_transformer_enc_dec_pipeline_vs_reference_fixture():
         for (_, _, _, h), (yseq, score, scores) in zip(res, gold):
             assert h.yseq.tolist() == yseq, dn
             assert abs(h.score - score) <= 1e-4 * max(1.0, abs(score))
+
+
+@pytest.mark.parametrize("dn", ["joint_lm", "att_lm", "ctc_lm"])
+def test_lm_fusion_oracle_vs_reference_fixture(dn):
+    """Groundwork for the LM row: TransformerLM as a full scorer (asr_inference.py:178-191) -- n-best lists and the
+    per-scorer score split of the reference Speech2Text with an LM (tests/golden/tiny_lm.npz)."""
+    import os
+
+    from oracle import encoder as OE
+    from oracle.lm import OracleLM
+    from oracle.search import OracleDecoder, batch_beam_search
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_lm.npz"))
+    cfg = dict(zip(z["cfg_keys"].tolist(), z["cfg_vals"].tolist()))
+    lmc = dict(zip(z["lm_keys"].tolist(), z["lm_vals"].tolist()))
+    w = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    beam, cw, lw, mlr = z[f"dec:{dn}:params"].tolist()
+    o = oracle.OracleSpeech2Text(cfg, {k: v for k, v in w.items() if not k.startswith("lm.")}, beam_size=int(beam), ctc_weight=cw, maxlenratio=mlr)
+    enc = o.encode(torch.from_numpy(z["wave"]))
+    logp = torch.log_softmax(OE.ctc_logits(enc, o.w), dim=-1)
+    dec = OracleDecoder(o.w, cfg["heads"], cfg["dec_layers"]) if cw != 1.0 else None
+    lm = OracleLM({k: v for k, v in w.items() if k.startswith("lm.")}, lmc["head"], lmc["layer"])
+    res = batch_beam_search(enc, dec, logp, beam_size=int(beam), ctc_weight=cw, vocab=cfg["vocab"], sos=cfg["vocab"] - 1, eos=cfg["vocab"] - 1,
+                            maxlenratio=mlr, lm=lm, lm_weight=lw)[:10]
+    n = int(z[f"dec:{dn}:n"])
+    assert len(res) == n
+    for i, h in enumerate(res):
+        assert h.yseq.tolist() == z[f"dec:{dn}:{i}:yseq"].tolist()
+        score = float(z[f"dec:{dn}:{i}:score"])
+        assert abs(h.score - score) <= 1e-4 * max(1.0, abs(score))
+        for k, ref in zip(("decoder", "ctc", "lm"), z[f"dec:{dn}:{i}:scores"]):
+            if not np.isnan(ref):
+                assert abs(h.scores[k] - ref) <= 1e-4 * max(1.0, abs(ref)), k
