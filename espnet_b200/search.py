@@ -270,6 +270,12 @@ class _SearchRun:
         if enc_split is None:
             enc_split = ops.split_from(enc.contiguous().view(U * Tmax, D))
         use_dec, use_ctc = bs.decoder is not None, bs.ctc is not None
+        if use_ctc and bool((maxlen > lens_cpu + 1).any()):
+            # The prefix scorer indexes its forward variables at [len(prefix) - 1] (ctc_prefix_score.py:147-172): the reference raises an IndexError
+            # in the middle of decoding once a hypothesis is two tokens longer than the encoder output; fail before touching device memory instead.
+            u = int(torch.nonzero(maxlen > lens_cpu + 1)[0])
+            raise IndexError(f"CTC prefix scoring cannot extend hypotheses beyond the encoder output length + 1: maxlen {int(maxlen[u])} for "
+                             f"{int(lens_cpu[u])} encoder frames (utterance {u}); lower maxlenratio or decode with ctc_weight=0")
         mode = 1 if (use_dec and use_ctc) else (0 if use_dec else 2)
         P = bs.pre_beam_size if mode == 1 else W
         st = bs._state(dev, U, Tmax, W, V, cap, mode, P, g)

@@ -255,3 +255,90 @@ def test_waveform_to_nbest_host_logic(case, dn, monkeypatch):
     for h, (yseq, score, _) in zip(hyps, gold):
         assert h.yseq.tolist() == yseq
         assert abs(h.score - score) <= 3e-4 * max(1.0, abs(score))
+
+
+def _random_model(cfg, seed):
+    import argparse
+
+    import espnet_b200
+    from gpu_util import random_weights, refbuild
+
+    w = random_weights(cfg, seed=seed)
+    model = espnet_b200.build_model(argparse.Namespace(**refbuild.model_yaml(cfg)))
+    model.load_state_dict(w, strict=True)
+    return model.eval(), {k: v.float() for k, v in w.items()}
+
+
+@pytest.mark.parametrize("cfg,lens", [
+    (dict(d_model=32, heads=1, ff=48, enc_layers=1, dec_layers=1, vocab=20, kernel=3), [7]),               # the shortest legal input: T = 1
+    (dict(d_model=32, heads=2, ff=48, enc_layers=2, dec_layers=1, vocab=20, kernel=7), [7, 30, 11]),       # T = 1, 6, 2 in one batch
+    (dict(d_model=64, heads=4, ff=64, enc_layers=1, dec_layers=1, vocab=20, kernel=15), [140, 8, 67, 139]),
+    (dict(d_model=32, heads=2, ff=32, enc_layers=1, dec_layers=1, vocab=20, kernel=31), [16, 15]),         # conv kernel wider than the sequence
+])
+def test_encoder_edge_shapes_host_logic(cfg, lens, monkeypatch):
+    from oracle import encoder as OE
+
+    emu_backend.install(monkeypatch)
+    model, w = _random_model(cfg, seed=1)
+    g = torch.Generator().manual_seed(0)
+    feats = torch.zeros(len(lens), max(lens), 80)
+    for i, n in enumerate(lens):
+        feats[i, :n] = torch.randn(n, 80, generator=g)
+    out, olens, _ = model.encoder(feats, torch.tensor(lens))
+    for i, n in enumerate(lens):
+        ref = OE.conformer_encode(feats[i, :n], w, cfg["heads"], cfg["enc_layers"])
+        assert int(olens[i]) == ref.shape[0]
+        np.testing.assert_allclose(out[i, : ref.shape[0]].numpy(), ref.numpy(), atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("lens", [[7], [11], [7, 23, 12]])
+@pytest.mark.parametrize("beam,cw,mlr,minr,pen,nl", [(2, 0.3, 0.0, 0.0, 0.0, False), (2, 0.0, 0.0, 0.0, 0.0, False), (2, 1.0, 0.0, 0.0, 0.0, False),
+                                                    (3, 0.3, 1.0, 0.5, 0.3, True)])
+def test_search_on_very_short_utterances_host_logic(lens, beam, cw, mlr, minr, pen, nl, monkeypatch):
+    """T = 1 .. 5 encoder frames (maxlen = T, minlen > 0, length bonus, normalised ranking): per-utterance results equal the oracle's.
+    Hypotheses CTC cannot align (score <= -1e9: ties of -7e9 that absorb every other term in fp32) are excluded from the comparison."""
+    from espnet_b200.search import BatchBeamSearch
+    from oracle import encoder as OE
+    from oracle.search import OracleDecoder, batch_beam_search
+
+    emu_backend.install_search(monkeypatch)
+    cfg = dict(d_model=32, heads=2, ff=48, enc_layers=1, dec_layers=1, vocab=12, kernel=7)
+    model, w = _random_model(cfg, seed=3)
+    g = torch.Generator().manual_seed(0)
+    feats = torch.zeros(len(lens), max(lens), 80)
+    for i, n in enumerate(lens):
+        feats[i, :n] = torch.randn(n, 80, generator=g)
+    bs = BatchBeamSearch(dict(decoder=model.decoder if cw != 1.0 else None, ctc=model.ctc), dict(decoder=1.0 - cw, ctc=cw, length_bonus=pen), beam,
+                         cfg["vocab"], model.sos, model.eos, token_list=model.token_list, pre_beam_score_key=None if cw == 1.0 else "full",
+                         normalize_length=nl)
+    enc, el, _ = model.encoder(feats, torch.tensor(lens))
+    res = bs.forward_batch(enc, el, model.enc_split(enc), mlr, minr)
+    for i, n in enumerate(lens):
+        renc = OE.conformer_encode(feats[i, :n], w, cfg["heads"], cfg["enc_layers"])
+        logp = torch.log_softmax(OE.ctc_logits(renc, w), -1)
+        dec = OracleDecoder(w, cfg["heads"], cfg["dec_layers"]) if cw != 1.0 else None
+        ref = batch_beam_search(renc, dec, logp, beam_size=beam, ctc_weight=cw, vocab=cfg["vocab"], sos=model.sos, eos=model.eos, maxlenratio=mlr,
+                                minlenratio=minr, penalty=pen, normalize_length=nl)
+        got = [h for h in res[i] if h.score > -1e9]
+        ref = [h for h in ref if h.score > -1e9]
+        assert [h.yseq.tolist() for h in got] == [h.yseq.tolist() for h in ref]
+        for a, b in zip(got, ref):
+            assert abs(a.score - b.score) <= 2e-4 * max(1.0, abs(b.score))
+
+
+def test_ctc_scoring_beyond_encoder_length_is_refused(monkeypatch):
+    """maxlen > T + 1 with a CTC scorer: the reference dies with an IndexError inside ctc_prefix_score.py once the prefix outgrows the
+    encoder output; here it is refused up front (the device kernels would index their state out of bounds)."""
+    from espnet_b200.search import BatchBeamSearch
+
+    emu_backend.install_search(monkeypatch)
+    cfg = dict(d_model=32, heads=2, ff=48, enc_layers=1, dec_layers=1, vocab=12, kernel=7)
+    model, _ = _random_model(cfg, seed=3)
+    feats = torch.randn(1, 11, 80, generator=torch.Generator().manual_seed(0))      # T = 2
+    enc, el, _ = model.encoder(feats, torch.tensor([11]))
+    mk = lambda cw: BatchBeamSearch(dict(decoder=model.decoder if cw != 1.0 else None, ctc=model.ctc), dict(decoder=1.0 - cw, ctc=cw), 2,  # noqa: E731
+                                    cfg["vocab"], model.sos, model.eos, pre_beam_score_key=None if cw == 1.0 else "full")
+    with pytest.raises(IndexError):
+        mk(0.3).forward_batch(enc, el, model.enc_split(enc), -4.0, 0.0)             # maxlen 4 > T + 1 = 3
+    assert len(mk(0.3).forward_batch(enc, el, model.enc_split(enc), -3.0, 0.0)) == 1   # maxlen = T + 1 is the last legal value
+    assert len(mk(0.0).forward_batch(enc, el, model.enc_split(enc), -6.0, 0.0)) == 1   # attention-only: no such limit
