@@ -120,6 +120,18 @@ class BatchBeamSearch(torch.nn.Module):
     @torch.no_grad()
     def forward_batch(self, enc, enc_lens, enc_split=None, maxlenratio=0.0, minlenratio=0.0, check_every=8):
         """enc (U, Tmax, D) CUDA, enc_lens (U,) -> list (per utterance) of n-best Hypothesis lists, sorted."""
+        out = self._search_once(enc, enc_lens, enc_split, maxlenratio, minlenratio, check_every)
+        # "there is no N-best results, perform recognition again with smaller minlenratio" (beam_search.py:462-471), per utterance
+        empty = [u for u, hyps in enumerate(out) if not hyps]
+        if empty and minlenratio >= 0.1:
+            idx = torch.tensor(empty, dtype=torch.long, device=enc.device)
+            lens_sub = enc_lens.detach().cpu()[torch.tensor(empty)]
+            retry = self.forward_batch(enc.index_select(0, idx).contiguous(), lens_sub, None, maxlenratio, max(0.0, minlenratio - 0.1), check_every)
+            for u, hyps in zip(empty, retry):
+                out[u] = hyps
+        return out
+
+    def _search_once(self, enc, enc_lens, enc_split, maxlenratio, minlenratio, check_every):
         U, Tmax, D = enc.shape
         bounds = self._group_bounds(U)
         if len(bounds) == 1:
@@ -243,10 +255,7 @@ class BatchBeamSearch(torch.nn.Module):
     def forward(self, x, maxlenratio=0.0, minlenratio=0.0):
         """Reference signature: one utterance, x (T, D) -> n-best list (beam_search.py:385-498)."""
         lens = torch.tensor([x.shape[0]], dtype=torch.int64)
-        res = self.forward_batch(x.unsqueeze(0).contiguous(), lens, None, maxlenratio, minlenratio)[0]
-        if not res and minlenratio >= 0.1:  # beam_search.py:462-471
-            return self.forward(x, maxlenratio, max(0.0, minlenratio - 0.1))
-        return res
+        return self.forward_batch(x.unsqueeze(0).contiguous(), lens, None, maxlenratio, minlenratio)[0]   # incl. the minlenratio retry
 
 
 class _SearchRun:

@@ -342,3 +342,74 @@ def test_ctc_scoring_beyond_encoder_length_is_refused(monkeypatch):
         mk(0.3).forward_batch(enc, el, model.enc_split(enc), -4.0, 0.0)             # maxlen 4 > T + 1 = 3
     assert len(mk(0.3).forward_batch(enc, el, model.enc_split(enc), -3.0, 0.0)) == 1   # maxlen = T + 1 is the last legal value
     assert len(mk(0.0).forward_batch(enc, el, model.enc_split(enc), -6.0, 0.0)) == 1   # attention-only: no such limit
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_randomised_search_settings_host_logic(seed, monkeypatch):
+    """Seeded sweep over model shapes, ragged batches and decode settings (beam 1-5, ctc_weight 0 .. 1, maxlenratio 0 / > 0 / < 0, minlenratio
+    incl. the "decode again with a smaller minlenratio" retry of beam_search.py:462-471, length bonus, normalised ranking, different
+    termination-poll intervals): every utterance's n-best list equals the oracle's."""
+    import random
+
+    from espnet_b200.search import BatchBeamSearch
+    from oracle import encoder as OE
+    from oracle.search import OracleDecoder, batch_beam_search
+
+    emu_backend.install_search(monkeypatch)
+    rnd = random.Random(seed)
+    checked = 0
+    for trial in range(12):
+        V, heads = rnd.choice([9, 12, 17]), rnd.choice([1, 2, 4])
+        cfg = dict(d_model=32, heads=heads, ff=rnd.choice([32, 48]), enc_layers=1, dec_layers=rnd.choice([1, 2]), vocab=V, kernel=rnd.choice([3, 7, 15]))
+        model, w = _random_model(cfg, seed=rnd.randrange(1000))
+        lens = [rnd.randrange(7, 60) for _ in range(rnd.choice([1, 2, 3]))]
+        g = torch.Generator().manual_seed(100 * seed + trial)
+        feats = torch.zeros(len(lens), max(lens), 80)
+        for i, n in enumerate(lens):
+            feats[i, :n] = torch.randn(n, 80, generator=g)
+        Ts = [((x - 1) // 2 - 1) // 2 for x in lens]
+        beam, cw = rnd.choice([1, 2, 3, 4, 5]), rnd.choice([0.0, 0.2, 0.5, 0.9, 1.0])
+        if cw not in (0.0, 1.0) and int(1.5 * beam) >= V:
+            beam = 2
+        mlr, minr = rnd.choice([0.0, 0.0, 0.5, 1.0, -2.0, -5.0]), rnd.choice([0.0, 0.0, 0.3, -1.0, -2.0])
+        pen, nl = rnd.choice([0.0, 0.0, 0.4, 1.5]), rnd.choice([False, True])
+        if cw != 0.0 and mlr < 0 and -mlr > min(Ts) + 1:
+            mlr = 0.0
+        bs = BatchBeamSearch(dict(decoder=model.decoder if cw != 1.0 else None, ctc=model.ctc), dict(decoder=1.0 - cw, ctc=cw, length_bonus=pen), beam,
+                             V, model.sos, model.eos, token_list=model.token_list, pre_beam_score_key=None if cw == 1.0 else "full", normalize_length=nl)
+        enc, el, _ = model.encoder(feats, torch.tensor(lens))
+        res = bs.forward_batch(enc, el, model.enc_split(enc), mlr, minr, check_every=rnd.choice([1, 3, 8]))
+        for i, n in enumerate(lens):
+            renc = OE.conformer_encode(feats[i, :n], w, heads, 1)
+            logp = torch.log_softmax(OE.ctc_logits(renc, w), -1)
+            dec = OracleDecoder(w, heads, cfg["dec_layers"]) if cw != 1.0 else None
+            ref = batch_beam_search(renc, dec, logp, beam_size=beam, ctc_weight=cw, vocab=V, sos=model.sos, eos=model.eos, maxlenratio=mlr,
+                                    minlenratio=minr, penalty=pen, normalize_length=nl)
+            got, ref = [h for h in res[i] if h.score > -1e9], [h for h in ref if h.score > -1e9]
+            assert [h.yseq.tolist() for h in got] == [h.yseq.tolist() for h in ref], (trial, cfg, lens, beam, cw, mlr, minr, pen, nl)
+            for a, b in zip(got, ref):
+                assert abs(a.score - b.score) <= 3e-4 * max(1.0, abs(b.score))
+            checked += 1
+    assert checked >= 12
+
+
+def test_minlenratio_retry_is_per_utterance(monkeypatch):
+    """maxlen 2 but minlen = int(0.3 T) > 2: nothing may end -> the reference decodes again with minlenratio lowered by 0.1 until something ends
+    (beam_search.py:462-471); in a batch only the utterances without a result are searched again."""
+    from espnet_b200.search import BatchBeamSearch
+
+    emu_backend.install_search(monkeypatch)
+    cfg = dict(d_model=32, heads=2, ff=48, enc_layers=1, dec_layers=1, vocab=17, kernel=7)
+    model, w = _random_model(cfg, seed=5)
+    g = torch.Generator().manual_seed(0)
+    lens = [59, 19]                 # T = 14 (minlen 4 > maxlen 2 -> retries) and T = 4 (minlen 1 -> ends in the first pass)
+    feats = torch.zeros(2, 59, 80)
+    for i, n in enumerate(lens):
+        feats[i, :n] = torch.randn(n, 80, generator=g)
+    enc, el, _ = model.encoder(feats, torch.tensor(lens))
+    bs = BatchBeamSearch(dict(decoder=model.decoder, ctc=None), dict(decoder=1.0, ctc=0.0), 2, cfg["vocab"], model.sos, model.eos)
+    first = bs._search_once(enc, el, model.enc_split(enc), -2.0, 0.3, 8)
+    assert first[0] == [] and len(first[1]) > 0
+    full = bs.forward_batch(enc, el, model.enc_split(enc), -2.0, 0.3)
+    assert len(full[0]) > 0 and [h.yseq.tolist() for h in full[1]] == [h.yseq.tolist() for h in first[1]]
+    assert all(len(h.yseq) == 4 for h in full[0])          # sos + 2 tokens + the eos appended at maxlen
