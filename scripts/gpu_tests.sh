@@ -1,10 +1,10 @@
 #!/bin/bash
 # Runs the -m gpu tests in separate processes (a CUDA fault in one must not hide the others); logs to gpurun_out/.
-# usage: scripts/gpu_tests.sh [stage ...]   stages: gemm_simt gemm_tc pipe_simt pipe_tc   (default: all)
+# usage: scripts/gpu_tests.sh [stage ...]   stages: gemm_simt gemm_tc gemm_tc2 pipe_simt pipe_tc pipe_tc2   (default: all)
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { echo BUILD FAILED; tail -20 gpurun_out/build.log; }
-stages=${@:-gemm_simt gemm_tc pipe_simt pipe_tc}
+stages=${@:-gemm_simt gemm_tc gemm_tc2 pipe_simt pipe_tc pipe_tc2}
 rc=0
 for st in $stages; do
   case $st in
