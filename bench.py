@@ -2,7 +2,7 @@
 """bench.py -- utterances/sec of the Speech2Text hot path (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            # espnet_b200 CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port) on the host cores
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU Speech2Text (oracle/_ref) on the host cores
 
 A "step" is one pass of the hot path over one batch of synthetic 16 kHz waveforms: BASELINE.json configs[1],
 Conformer-large (12L/512d/8h, ff 2048, conv2d, macaron, rel-pos latest, kernel 31) + 6L Transformer decoder,
@@ -59,57 +59,104 @@ def model_weights(cfg):
     return _WEIGHTS[key]
 
 
-CPU_SAMPLE_STEPS = 8   # beam-search steps actually run on the CPU per sample; the remaining steps are extrapolated linearly
-_CPU_THREADS = [None]
+# ----------------------------------------------------------------------------------------------- reference CPU path
+# The reference's own espnet2.bin.asr_inference.Speech2Text (unmodified files under oracle/_ref, made by oracle/install_ref.py where
+# /root/reference is mounted; it travels to the GPU box with the snapshot), batch-1 as the reference decodes, FULL search (all
+# |maxlenratio| steps) -- no extrapolation.  The reference parallelises decoding by running independent processes over slices of the key
+# file (egs2/TEMPLATE/asr1/asr.sh:1591-1618, `inference_nj`): the CPU arm does the same with REF_WORKERS processes x REF_THREADS torch
+# threads (fixed numbers, stated in the line; one process with all host threads is far slower: the search is thousands of tiny ops).
+REF_THREADS = 8
 
 
-def cpu_threads(cfg):
-    """Thread count for the CPU path.  The reference's search is thousands of tiny ATen ops per step; on a many-core host the
-    default (all cores) thread pool makes them slower, so pick the fastest of {8, 16, 32, all} on a 2-second probe utterance."""
-    if _CPU_THREADS[0] is None:
+def ref_workers():
+    ncpu = os.cpu_count() or 1
+    return int(os.environ.get("ESPB_REF_WORKERS", max(1, min(8, ncpu // (2 * REF_THREADS)))))
+
+
+def ref_kind():
+    from oracle import install_ref
+
+    return "reference" if install_ref.available() else "port"
+
+
+def _ref_worker(rank, cfg, wfile, beam, ctcw, mlr, inq, outq):
+    """One decoding process: builds the CPU Speech2Text once, then decodes the waveforms it is sent."""
+    import torch as _t
+
+    _t.set_num_threads(REF_THREADS)
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    weights = _t.load(wfile)
+    from oracle import install_ref
+
+    if install_ref.available():
+        install_ref.activate()
+        import logging
+
+        import refbuild
+
+        logging.disable(logging.WARNING)
+        s2t = refbuild.build_reference(cfg, seed=0, beam_size=beam, ctc_weight=ctcw, maxlenratio=mlr, nbest=1)
+        s2t.asr_model.load_state_dict(weights, strict=True)       # same weights as the CUDA arm (parity check of the bench)
+        s2t.asr_model.eval()
+        run = lambda w: s2t(w.numpy())  # noqa: E731
+    else:
         import oracle
 
-        ncpu = os.cpu_count() or 1
-        cands = sorted({c for c in (8, 16, 32, ncpu) if c <= ncpu}) or [ncpu]
-        if len(cands) > 1:
-            o = oracle.OracleSpeech2Text(cfg, model_weights(cfg), beam_size=4, ctc_weight=0.3, maxlenratio=-2.0, nbest=1)
-            wave = waveforms(1, 2 * 16000, offset=999)[0]
-            best = (None, float("inf"))
-            for c in cands:
-                torch.set_num_threads(c)
-                o(wave)
-                t0 = time.perf_counter()
-                o(wave)
-                dt = time.perf_counter() - t0
-                if dt < best[1]:
-                    best = (c, dt)
-            _CPU_THREADS[0] = best[0]
-        else:
-            _CPU_THREADS[0] = cands[0]
-    torch.set_num_threads(_CPU_THREADS[0])
-    return _CPU_THREADS[0]
+        o = oracle.OracleSpeech2Text(cfg, weights, beam_size=beam, ctc_weight=ctcw, maxlenratio=mlr, nbest=1)
+        run = lambda w: o(w)  # noqa: E731
+    outq.put(("ready", rank))
+    while True:
+        item = inq.get()
+        if item is None:
+            return
+        idx, wave = item
+        t0 = time.perf_counter()
+        res = run(wave)
+        dt = time.perf_counter() - t0
+        outq.put((idx, dt, res[0][3].yseq.tolist() if res else None, float(res[0][3].score) if res else None))
 
 
-def cpu_sample_seconds(cfg, secs, beam, ctcw, mlr, wave):
-    """Reference CPU path (oracle port) on ONE utterance, bounded: the encoder in full plus the first CPU_SAMPLE_STEPS of the
-    |maxlenratio| beam-search steps; the per-utterance time is encoder + search * (steps / CPU_SAMPLE_STEPS).
-    Returns (estimated seconds per utterance, description, oracle result of the truncated search)."""
-    import oracle
+class RefPool:
+    """REF_WORKERS reference decoders; decode(waves) runs one utterance per worker concurrently and returns the wall time."""
 
-    total_steps = int(-mlr)
-    run_steps = min(CPU_SAMPLE_STEPS, total_steps)
-    o = oracle.OracleSpeech2Text(cfg, model_weights(cfg), beam_size=beam, ctc_weight=ctcw, maxlenratio=-float(run_steps), nbest=1)
-    t0 = time.perf_counter()
-    o.encode(wave)
-    t_enc = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    res = o(wave)
-    t_all = time.perf_counter() - t0
-    t_search = max(t_all - t_enc, 0.0)
-    est = t_enc + t_search * (total_steps / run_steps)
-    desc = (f"1 utterance of {secs} s, batch-1: encoder in full ({t_enc:.1f} s) + first {run_steps} of {total_steps} beam-search steps "
-            f"({t_search:.1f} s), search time scaled x{total_steps / run_steps:.0f}")
-    return est, desc, res
+    def __init__(self, cfg, beam, ctcw, mlr, workers):
+        import tempfile
+
+        import torch.multiprocessing as mp
+
+        self.n = workers
+        ctx = mp.get_context("spawn")
+        self.wfile = os.path.join(tempfile.mkdtemp(prefix="espb_ref_"), "weights.pt")
+        torch.save(model_weights(cfg), self.wfile)
+        self.inq = [ctx.Queue() for _ in range(workers)]
+        self.outq = ctx.Queue()
+        self.procs = [ctx.Process(target=_ref_worker, args=(r, cfg, self.wfile, beam, ctcw, mlr, self.inq[r], self.outq), daemon=True)
+                      for r in range(workers)]
+        for p in self.procs:
+            p.start()
+        for _ in range(workers):
+            assert self.outq.get(timeout=900)[0] == "ready"
+
+    def decode(self, waves):
+        assert len(waves) == self.n
+        t0 = time.perf_counter()
+        for r, w in enumerate(waves):
+            self.inq[r].put((r, w))
+        out = [self.outq.get(timeout=3600) for _ in range(self.n)]
+        wall = time.perf_counter() - t0
+        return wall, sorted(out)
+
+    def close(self):
+        for q in self.inq:
+            q.put(None)
+        for p in self.procs:
+            p.join(timeout=30)
+
+
+def ref_sample_desc(secs, mlr, workers, beam):
+    return (f"{workers} utterance(s) of {secs} s decoded concurrently, one per process ({workers} processes x {REF_THREADS} torch threads of "
+            f"{os.cpu_count()} host threads), each batch-1 through {'espnet2.bin.asr_inference.Speech2Text (oracle/_ref)' if ref_kind() == 'reference' else 'the oracle port'}: "
+            f"encoder + the full {int(-mlr)}-step joint beam-{beam} search, no extrapolation")
 
 
 class ClockSampler:
@@ -170,31 +217,46 @@ def measured_peaks():
 
 # ----------------------------------------------------------------------------------------------- reference arm (CPU)
 def run_reference(args, rank, world):
-    """Reference CPU path = the oracle port (pure torch CPU restatement; the reference itself is Python and cannot
-    travel to the GPU box).  One step = one utterance of the workload decoded batch-1, as Speech2Text does."""
+    """Reference arm: one step = REF_WORKERS utterances of the workload decoded concurrently by the reference's own CPU Speech2Text
+    (a bounded sample of the 64-utterance batch).  value = utterances / wall time.  A CPU decode needs one warm-up, not W: min(W, 1)
+    are run.  ESPB_REF_BUDGET_S (default 330) bounds the run: if the next timed step would overrun it, the run stops and reports the
+    steps it completed (stated in the line)."""
     if rank != 0:
         return
     cfg, secs, batch, beam, ctcw, mlr = WORKLOADS[args.workload]
-    cpu_threads(cfg)
-    waves = waveforms(args.warmup + args.steps, secs * 16000)
-    desc = ""
-    for i in range(args.warmup):
-        cpu_sample_seconds(cfg, secs, beam, ctcw, mlr, waves[i])
-    est_total = 0.0
+    workers = ref_workers()
+    t_start = time.perf_counter()
+    pool = RefPool(cfg, beam, ctcw, mlr, workers)
+    warm = min(args.warmup, 1)
+    waves = waveforms((warm + args.steps) * workers, secs * 16000)
+    budget = float(os.environ.get("ESPB_REF_BUDGET_S", 330))
+    k = 0
+    for i in range(warm):
+        pool.decode(list(waves[k:k + workers])); k += workers
+    walls = []
     for i in range(args.steps):
-        est, desc, _ = cpu_sample_seconds(cfg, secs, beam, ctcw, mlr, waves[args.warmup + i])
-        est_total += est
-    dt = est_total
-    ups = args.steps / dt
+        est = max(walls) if walls else 0.0
+        if walls and (time.perf_counter() - t_start) + est > budget:
+            break
+        w, _ = pool.decode(list(waves[k:k + workers])); k += workers
+        walls.append(w)
+    pool.close()
+    done = len(walls)
+    dt = sum(walls)
+    ups = done * workers / dt
+    desc = ref_sample_desc(secs, mlr, workers, beam)
     line = {
-        "impl": "reference", "metric": METRIC, "value": ups, "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": ups, "unit": "utterances/s", "n_gpus": args.gpus, "steps": done,
+        "warmup": warm, "ms_per_step": 1000.0 * dt / done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "rtf": (dt / args.steps) / secs,
-        "config": {"workload": args.workload, "sample": "per step: " + desc, "beam": beam,
-                   "ctc_weight": ctcw, "maxlenratio": mlr, "utt_seconds": secs},
-        "cpu_baseline": {"value": ups, "unit": "utterances/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{args.steps} steps, each: {desc}; {args.warmup} warm-up"},
+        "rtf": (dt / (done * workers)) / secs,
+        "config": {"workload": args.workload, "sample": "per step: " + desc, "beam": beam, "global_batch": batch,
+                   "ctc_weight": ctcw, "maxlenratio": mlr, "utt_seconds": secs, "vocab": cfg["vocab"],
+                   "steps_requested": args.steps, "warmup_requested": args.warmup,
+                   "note": (f"stopped after {done} of {args.steps} steps (ESPB_REF_BUDGET_S={budget:.0f} s)" if done < args.steps else "all requested steps timed")
+                           + "; a CPU decode needs no more than one warm-up"},
+        "cpu_baseline": {"value": ups, "unit": "utterances/s", "cores": workers * REF_THREADS, "kind": ref_kind(),
+                         "sample": f"{done} steps, each: {desc}; {warm} warm-up"},
         "e2e": {"value": ups, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -393,10 +455,28 @@ def run_b200(args, rank, local_rank, world):
     }
     print("[bench] gpu arm done: " + json.dumps(line), file=sys.stderr, flush=True)
     if args.cpu_baseline and world == 1:   # the host-core baseline is reported by the single-GPU run only
-        cpu_threads(cfg)
-        est, desc, _ = cpu_sample_seconds(cfg, secs, beam, ctcw, mlr, host[0])
-        line["cpu_baseline"] = {"value": 1.0 / est, "unit": "utterances/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": desc + f"; no warm-up; {torch.get_num_threads()} of {os.cpu_count()} host threads (fastest of 8/16/32/all on a probe)"}
+        workers = ref_workers()
+        pool = RefPool(cfg, beam, ctcw, mlr, workers)
+        wall, out = pool.decode([host[i] for i in range(workers)])      # the first `workers` utterances of this rank's batch, no warm-up
+        pool.close()
+        line["cpu_baseline"] = {"value": workers / wall, "unit": "utterances/s", "cores": workers * REF_THREADS, "kind": ref_kind(),
+                                "sample": ref_sample_desc(secs, mlr, workers, beam) + "; one step, no warm-up"}
+        # parity of the benchmarked configuration, enforced by the bench itself: the CUDA n-best of the same utterances (from the last timed
+        # end-to-end step) against the reference CPU result -- identical token sequences, scores within rtol 2e-4
+        eq, rel = True, 0.0
+        for idx, _, yseq, score in out:
+            g = res[idx][0][3] if res[idx] else None
+            if g is None or yseq is None:
+                eq = eq and (g is None and yseq is None)
+                continue
+            eq = eq and (g.yseq.tolist() == yseq)
+            rel = max(rel, abs(float(g.score) - score) / max(1.0, abs(score)))
+        line["parity_check"] = {"against": ref_kind(), "utterances": workers, "search_steps": int(-mlr), "yseq_equal": bool(eq), "score_rel_err": rel,
+                                "tolerance": "identical yseq, score rtol 2e-4"}
+        if not eq or rel > 2e-4:
+            print(json.dumps(line), flush=True)
+            print("[bench] PARITY CHECK FAILED: " + json.dumps(line["parity_check"]), file=sys.stderr, flush=True)
+            sys.exit(3)
     print(json.dumps(line), flush=True)
 
 

@@ -103,6 +103,15 @@ def build_model_from_file(config_file, model_file=None, device="cuda"):
     return model, args
 
 
+# keywords of the reference constructor that would change the result if honoured (refused unless left at their defaults) ...
+_REFUSED_KWARGS = {"lm_train_config", "lm_file", "ngram_file", "transducer_conf", "streaming", "quantize_asr_model", "quantize_lm",
+                   "enh_s2t_task", "hugging_face_decoder", "multi_asr", "partial_ar", "lid_prompt",
+                   "lang_prompt_token", "nlp_prompt_token", "prompt_token_file", "time_sync"}
+# ... and those that cannot (accepted without a warning)
+_HARMLESS_KWARGS = {"ngram_scorer", "quantize_modules", "quantize_dtype", "search_beam_size", "decoder_text_length_limit", "encoded_feat_length_limit", "hugging_face_decoder_conf",
+                    "threshold_probability", "max_seq_len", "max_mask_parallel"}
+
+
 class Speech2Text:
     def __init__(self, asr_train_config=None, asr_model_file=None, device: str = "cuda", dtype: str = "float32",
                  beam_size: int = 20, ctc_weight: float = 0.5, lm_weight: float = 1.0, ngram_weight: float = 0.9,
@@ -111,6 +120,14 @@ class Speech2Text:
                  asr_model: Optional[ESPnetASRModel] = None, asr_train_args=None, **unused):
         if dtype != "float32":
             raise NotImplementedError("espnet_b200 computes in float32 (the reference's inference dtype)")
+        # Reference keywords (asr_inference.py:86-127) that select a different decoding algorithm must not be dropped silently.
+        refused = {k: v for k, v in unused.items()
+                   if k in _REFUSED_KWARGS and v not in (None, False, "", {}, [])}
+        if refused:
+            raise NotImplementedError("espnet_b200.Speech2Text does not implement: " + ", ".join(f"{k}={v!r}" for k, v in sorted(refused.items())))
+        ignored = sorted(k for k in unused if k not in _REFUSED_KWARGS and k not in _HARMLESS_KWARGS)
+        if ignored:
+            logger.warning("espnet_b200.Speech2Text ignores these keyword arguments: " + ", ".join(ignored))
         if not str(device).startswith("cuda"):
             raise RuntimeError("espnet_b200 has no CPU path: device must be a CUDA device")
         lib.load()  # fail loudly if the CUDA library is missing

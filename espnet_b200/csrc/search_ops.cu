@@ -581,6 +581,7 @@ __device__ __forceinline__ float ctc_phi(const float4* __restrict__ rp, int t, b
 // so it is a reduction over t: one warp per (slot, candidate), lanes stride t.  Must be called by a full warp.
 __device__ __forceinline__ float ctc_log_psi_warp(const float* __restrict__ x, long long st_t, long long st_c, int T, int blank, int eos,
                                                   const float4* __restrict__ rp, int c, int last, int out_len, int lane) {
+  if (T <= 0) return LOGZERO;                                              // empty encoder output (refused on the host; never index rp[-1])
   if (c == eos) return __ldg(rp + (T - 1)).z;                             // (:184-185) r_sum[T-1]
   if (c == blank) return LOGZERO;                                          // (:187-189)
   const int start = max(out_len, 1);
@@ -638,7 +639,8 @@ __global__ void __launch_bounds__(128) ctc_score_dense_kernel(const float* __res
   const float* x = logp + (long long)u * Tmax * V;
   const float4* rp = reinterpret_cast<const float4*>(r_prev) + (long long)s * Tmax;
   float v;
-  if (c == eos) v = __ldg(rp + (T - 1)).z;
+  if (T <= 0) v = LOGZERO;
+  else if (c == eos) v = __ldg(rp + (T - 1)).z;
   else if (c == blank) v = LOGZERO;
   else {
     const int start = max(out_len, 1);
@@ -814,8 +816,10 @@ __global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restric
   const bool same = (c == last);
   const int start = max(out_len, 1);
   float rn = (out_len == 0) ? x[c * st_c] : LOGZERO, rb = LOGZERO;   // r[start-1]
-  for (int t = lane; t < start - 1; t += 32) ro[t] = Z4;
-  if (lane == 0) ro[start - 1] = make_float4(rn, rb, logaddexp(rn, rb), 0.f);
+  // a prefix longer than the encoder output (start - 1 >= T) has no valid frame left: the state is all-logzero (the reference's
+  // r[start - 1] raises an IndexError there, ctc_prefix_score.py:147; the host reports it per utterance after the search)
+  for (int t = lane; t < min(start - 1, Tmax); t += 32) ro[t] = Z4;
+  if (lane == 0 && start - 1 < Tmax) ro[start - 1] = (start - 1 < T) ? make_float4(rn, rb, logaddexp(rn, rb), 0.f) : Z4;
   for (int t0 = start; t0 < T; t0 += 32) {
     const int t = t0 + lane;
     float phi = LOGZERO, xc = 0.f, xb = 0.f;

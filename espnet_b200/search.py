@@ -62,8 +62,9 @@ class BatchBeamSearch(torch.nn.Module):
             raise NotImplementedError("beam_size > 32 (the per-utterance beam selection runs in one warp)")
 
     # ---------------------------------------------------------------- search state (cached per shape so that CUDA graphs can be reused)
-    def _state(self, dev, U, Tmax, W, V, cap, mode, P, g=0):
-        key = (str(dev), U, Tmax, W, V, cap, mode, P, g)
+    def _state(self, dev, U, Tmax, W, V, cap, mode, P, g=0, end_detect=0):
+        # end_detect is baked into the captured CUDA graphs (by-value kernel argument of beam_select): it is part of the key
+        key = (str(dev), U, Tmax, W, V, cap, mode, P, g, end_detect)
         cache = getattr(self, "_state_cache", None)
         if cache is None:
             cache = self._state_cache = {}
@@ -279,17 +280,12 @@ class _SearchRun:
         if enc_split is None:
             enc_split = ops.split_from(enc.contiguous().view(U * Tmax, D))
         use_dec, use_ctc = bs.decoder is not None, bs.ctc is not None
-        if use_ctc and bool((maxlen > lens_cpu + 1).any()):
-            # The prefix scorer indexes its forward variables at [len(prefix) - 1] (ctc_prefix_score.py:147-172): the reference raises an IndexError
-            # in the middle of decoding once a hypothesis is two tokens longer than the encoder output; fail before touching device memory instead.
-            u = int(torch.nonzero(maxlen > lens_cpu + 1)[0])
-            raise IndexError(f"CTC prefix scoring cannot extend hypotheses beyond the encoder output length + 1: maxlen {int(maxlen[u])} for "
-                             f"{int(lens_cpu[u])} encoder frames (utterance {u}); lower maxlenratio or decode with ctc_weight=0")
         mode = 1 if (use_dec and use_ctc) else (0 if use_dec else 2)
         P = bs.pre_beam_size if mode == 1 else W
-        st = bs._state(dev, U, Tmax, W, V, cap, mode, P, g)
+        self.end_detect = 1 if maxlenratio == 0.0 else 0
+        st = bs._state(dev, U, Tmax, W, V, cap, mode, P, g, self.end_detect)
         self.U, self.W, self.V, self.n, self.Tmax, self.cap, self.mode, self.P, self.st = U, W, V, n, Tmax, cap, mode, P, st
-        self.maxlen, self.use_dec, self.use_ctc, self.dev = maxlen, use_dec, use_ctc, dev
+        self.maxlen, self.use_dec, self.use_ctc, self.dev, self.lens_cpu = maxlen, use_dec, use_ctc, dev, lens_cpu
         self.finished, self.steps_run = False, 0
 
         # ---- (re)initialise the state in place: one hypothesis [sos] per utterance (batch_beam_search.py:124-153)
@@ -318,7 +314,6 @@ class _SearchRun:
                 self.logp_tok, self.tok_major = st["logp_ctc_t"], 1
                 call("espb_transpose_tv_f32", ptr(self.logp_ctc), U, Tmax, V, ptr(self.logp_tok))
                 _count()
-        self.end_detect = 1 if maxlenratio == 0.0 else 0
         self.side = bs._side_stream(dev, g) if (use_ctc and use_dec) else None
         self.buf_ver = (getattr(bs.decoder, "buf_version", 0), id(bs.decoder._packed)) if use_dec else None
 
@@ -429,5 +424,19 @@ class _SearchRun:
 
     def collect(self):
         st = self.st
+        if self.use_ctc:
+            # The prefix scorer indexes its forward variables at [len(prefix) - 1] (ctc_prefix_score.py:147-172): the reference raises an
+            # IndexError in the middle of decoding once a LIVE hypothesis is two tokens longer than the encoder output.  The kernels keep an
+            # all-logzero state there instead of indexing out of bounds; an utterance is reported only if that really happened, i.e. a
+            # hypothesis of it was still being extended at step T + 1 (back-pointer rows of dead slots are -1).
+            over = [u for u in range(self.U) if int(self.maxlen[u]) > int(self.lens_cpu[u]) + 1 and self.steps_run > int(self.lens_cpu[u]) + 1]
+            if over:
+                bpp = st["bp_parent"][: self.steps_run].cpu()
+                bad = [u for u in over if bool((bpp[int(self.lens_cpu[u]) + 1, u * self.W:(u + 1) * self.W] >= 0).any())]
+                if bad:
+                    u = bad[0]
+                    raise IndexError(f"CTC prefix scoring cannot extend hypotheses beyond the encoder output length + 1: utterance(s) {bad} of this group "
+                                     f"still had live hypotheses at step {int(self.lens_cpu[u]) + 1} ({int(self.lens_cpu[u])} encoder frames, maxlen "
+                                     f"{int(self.maxlen[u])}); lower maxlenratio or decode with ctc_weight=0")
         return self.bs._collect(self.U, self.W, self.steps_run, self.maxlen, st["bp_parent"], st["bp_token"], st["e_count"], st["e_step"],
                                 st["e_slot"], st["e_score"], st["e_dec"], st["e_ctc"])

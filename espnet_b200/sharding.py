@@ -3,12 +3,17 @@
 The reference parallelises decoding only by splitting the key file over OS processes (egs2/TEMPLATE/asr1/asr.sh:1591-1618)
 and concatenating result files; here rank r decodes utterances r, r+world, ... and the n-best lists are gathered once with
 torch.distributed (NCCL on GPUs, gloo in the CPU tests).  Records are int32 [n_local_padded, nbest, 2 + max_tokens]:
-(n_tokens, float32 score bits, tokens..., -1 padding); rows of ranks with fewer utterances are marked n_tokens = -1.
+(n_tokens, float32 score bits, tokens..., -1 padding).  Unused n-best entries have n_tokens = -1; padding ROWS (ranks holding fewer
+utterances) have n_tokens = -2 in entry 0, so that a real utterance with an empty n-best list (nothing ended, beam_search.py:467-471)
+keeps its row and later utterances are not shifted.
 """
 from typing import List, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+PAD_ROW = -2   # n_tokens marker of a padding row (entry 0)
 
 
 def shard_indices(n_utts: int, rank: int, world: int) -> List[int]:
@@ -19,6 +24,7 @@ def pack_hypotheses(nbest_lists: Sequence[Sequence[Tuple[List[int], float]]], nb
                     device="cpu") -> torch.Tensor:
     rows = len(nbest_lists) if rows is None else rows
     rec = torch.full((rows, nbest, 2 + max_tokens), -1, dtype=torch.int32)
+    rec[len(nbest_lists):, 0, 0] = PAD_ROW
     for i, hyps in enumerate(nbest_lists):
         for j, (toks, score) in enumerate(list(hyps)[:nbest]):
             toks = list(toks)[:max_tokens]
@@ -40,7 +46,7 @@ def unpack_hypotheses(rec: torch.Tensor, nbest: int):
                 continue
             score = float(rec[i, j, 1].view(torch.float32))
             hyps.append((rec[i, j, 2:2 + n].tolist(), score))
-        if hyps or int(rec[i, 0, 0]) >= 0:
+        if int(rec[i, 0, 0]) != PAD_ROW:
             out.append(hyps)
     return out
 
@@ -55,6 +61,7 @@ def gather_hypotheses(rec: torch.Tensor, world: int) -> torch.Tensor:
     rows = int(n.item())
     if rec.shape[0] < rows:
         pad = torch.full((rows - rec.shape[0],) + tuple(rec.shape[1:]), -1, dtype=rec.dtype, device=rec.device)
+        pad[:, 0, 0] = PAD_ROW
         rec = torch.cat([rec, pad], 0)
     out = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
     dist.all_gather_into_tensor(out.view(world * rows, *rec.shape[1:]), rec.contiguous())

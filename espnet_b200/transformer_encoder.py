@@ -119,9 +119,14 @@ class TransformerEncoder(torch.nn.Module):
         xs_pad = xs_pad.contiguous().float()
         B, Tf, F = xs_pad.shape
         assert F == self.idim
-        if Tf < 7:  # check_short_utt (subsampling.py:43-44), transformer_encoder.py:253-262
-            raise TooShortUttError(f"has {Tf} frames and is too short for subsampling (it needs more than 7 frames), "
-                                   "return empty results", Tf, 7)
+        # check_short_utt (subsampling.py:43-44), transformer_encoder.py:253-262: the reference decodes one utterance per call, so the limit applies to every
+        # utterance of a ragged batch, not to the padded length (an utterance with < 7 frames would get olens 0)
+        min_len = int(torch.as_tensor(ilens).min()) if torch.as_tensor(ilens).numel() else Tf
+        if Tf < 7 or min_len < 7:
+            size = min(Tf, min_len)
+            which = "" if Tf < 7 else f" (utterance {int(torch.as_tensor(ilens).argmin())} of the batch)"
+            raise TooShortUttError(f"has {size} frames and is too short for subsampling (it needs more than 7 frames), "
+                                   f"return empty results{which}", size, 7)
         D, H, U = self._output_size, self.heads, self.units
         C, dk = D, D // H
         F1, F2 = pk["F1"], pk["F2"]

@@ -298,6 +298,8 @@ def _transpose_tv(x, U, Tmax, V, xt):
 
 
 def _log_psi(x, T, blank, eos, rp, c, last, out_len):
+    if T <= 0:
+        return LOGZERO
     if c == eos:
         return float(rp[T - 1, 2])
     if c == blank:
@@ -347,7 +349,8 @@ def _ctc_advance(logp, U, Tmax, V, lens, blank, eos, W, r_prev, parent, par_last
         start = max(out_len, 1)
         rn, rb = (x(0, c) if out_len == 0 else LOGZERO), LOGZERO
         ro[s] = Z4
-        ro[s, start - 1] = torch.tensor([rn, rb, _lae(rn, rb), 0.0])
+        if start - 1 < T:      # a prefix longer than the encoder output keeps an all-logzero state (ctc_advance_kernel)
+            ro[s, start - 1] = torch.tensor([rn, rb, _lae(rn, rb), 0.0])
         for t in range(start, T):
             phi = float(rp[p, t - 1, 1]) if c == last else float(rp[p, t - 1, 2])
             rn, rb = _lae(rn, phi) + x(t, c), _lae(rn, rb) + x(t, blank)

@@ -1,7 +1,8 @@
 """-m gpu parity tests: CUDA path (through the C-ABI library) vs the golden fixtures and the CPU oracle.
 
-Tolerances (fp32 path, error-compensated 3xTF32 GEMMs): features atol 5e-4 on log-mel; encoder outputs
-atol 2e-3 on O(1) activations (measured error is printed); CTC-greedy token ids bit-exact; beam-search
+Tolerances (fp32 path, error-compensated 3xTF32 GEMMs): features atol 5e-4 on log-mel; encoder outputs / CTC logits
+atol 1e-4 on O(1) activations with the default GEMM (chunked fp32 promotion, measured ~5e-6) and the FFMA GEMM, 5e-4 with the
+first 1-CTA kernel that accumulates all of K in TMEM (measured ~4e-5); CTC-greedy token ids bit-exact; beam-search
 token sequences identical and scores within rtol 2e-4 (the reference's own cached-vs-uncached decoder
 tolerance is rtol 1e-4, test/espnet2/legacy/test_transformer_decode.py:9).
 """
@@ -30,6 +31,13 @@ def gemm_mode(request):
     ops.set_gemm_mode(request.param)
     yield request.param
     ops.set_gemm_mode(old)
+
+
+def enc_tol(mode=None):
+    """Encoder / logits tolerance by GEMM kernel (see the module docstring)."""
+    from espnet_b200 import ops
+
+    return 5e-4 if (mode or ops.gemm_mode()) == "tc" else 1e-4
 
 
 def _maxerr(a, b):
@@ -94,16 +102,17 @@ def test_encoder_vs_golden(case, gemm_mode):
     errs = [_maxerr(t[0], z[f"layer{i}"]) for i, t in enumerate(model.encoder.trace)]
     print(f"[{case}/{gemm_mode}] per-stage max abs err:", ["%.2e" % e for e in errs])
     assert olens.tolist() == [z["enc"].shape[0]]
-    assert max(errs) < 2e-3, errs
+    tol = enc_tol(gemm_mode)
+    assert max(errs) < tol, errs
     e = _maxerr(enc[0], z["enc"])
     print(f"[{case}/{gemm_mode}] encoder out max abs err {e:.3e}")
-    assert e < 2e-3
+    assert e < tol
     lg = model.ctc.logits(enc, model.enc_split(enc))
     e = _maxerr(lg[0], z["ctc_logits"])
     print(f"[{case}/{gemm_mode}] ctc logits max abs err {e:.3e}")
-    assert e < 2e-3
+    assert e < tol
     lp = model.ctc.log_softmax(enc)
-    assert _maxerr(lp[0], z["ctc_logp"]) < 2e-3
+    assert _maxerr(lp[0], z["ctc_logp"]) < tol
     assert model.ctc.argmax(enc)[0].cpu().tolist() == z["ctc_argmax"].tolist()
 
 
@@ -131,7 +140,7 @@ def test_encoder_batch_and_ragged_vs_oracle(gemm_mode):
             assert int(elens[i]) == ref.shape[0]
             e = _maxerr(enc[i, : ref.shape[0]], ref)
             print(f"[{gemm_mode}] lens={lens} utt{i} enc max abs err {e:.3e}")
-            assert e < 2e-3
+            assert e < enc_tol(gemm_mode)
             am, ids = OE.ctc_greedy(ref, o.w)
             logits = OE.ctc_logits(ref, o.w)
             top2 = logits.topk(2, dim=-1)[0]
@@ -207,7 +216,7 @@ def test_config0_ctc_greedy_8x5s_vs_oracle():
         margin = (top2[:, 0] - top2[:, 1]).min().item()
         _, ids = OE.ctc_greedy(ref_enc, o.w)
         print(f"utt{i}: logit max abs err {err:.2e}, min top-2 margin {margin:.2e}, tokens {len(ids)}")
-        assert err < 2e-3
+        assert err < 2 * enc_tol()          # logits of a V=5000 head on O(1) encoder outputs
         if margin > 20 * err:
             assert got[i] == ids.tolist()
             checked += 1
@@ -314,7 +323,7 @@ def test_speech2text_with_global_mvn_vs_oracle(tmp_path):
     mean, std = OF.global_mvn_stats(stats)
     fn = OF.global_mvn(feats[None], torch.tensor([feats.shape[0]]), mean, std)[0]
     ref = OE.conformer_encode(fn, w, cfg["heads"], cfg["enc_layers"])
-    assert _maxerr(enc[0, : ref.shape[0]], ref) < 2e-3
+    assert _maxerr(enc[0, : ref.shape[0]], ref) < enc_tol()
 
 
 @pytest.mark.parametrize("groups", [2, 3])

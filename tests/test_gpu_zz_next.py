@@ -1,14 +1,14 @@
 """Next scope row: TransformerEncoder (abs-pos) on the CUDA path vs the reference fixture and the oracle.
 
-OPT-IN: the oracle side is pinned to the reference on CPU (tests/test_oracle_golden.py), but this CUDA path has not been run on a
-B200 yet, so these tests only run with ESPB_TEST_NEXT=1 and are otherwise skipped (they must not colour the hot-path suite)."""
+The oracle side is pinned to the reference on CPU (tests/test_oracle_golden.py).  Tolerance: encoder outputs atol 1e-4 (default GEMM)."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("ESPB_TEST_NEXT") != "1", reason="set ESPB_TEST_NEXT=1 (not yet validated on a B200)")]
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
 
 
 def _load():
@@ -37,8 +37,8 @@ def test_transformer_encoder_vs_reference_fixture():
     for i in range(cfg["layers"]):
         err = float((enc.trace[i + 1][0].cpu() - torch.from_numpy(z[f"layer{i + 1}"])).abs().max())
         print(f"layer {i + 1} max abs err {err:.3e}")
-        assert err < 2e-3
-    assert float((out[0].cpu() - torch.from_numpy(z["out"])).abs().max()) < 2e-3
+        assert err < TOL
+    assert float((out[0].cpu() - torch.from_numpy(z["out"])).abs().max()) < TOL
 
 
 def test_transformer_encoder_ragged_batch_vs_oracle():
@@ -55,7 +55,9 @@ def test_transformer_encoder_ragged_batch_vs_oracle():
     for i, n in enumerate(lens):
         ref = TE.transformer_encode(feats[i, :n], w, cfg["heads"], cfg["layers"])
         assert int(olens[i]) == ref.shape[0]
-        assert float((out[i, : ref.shape[0]].cpu() - ref).abs().max()) < 2e-3
+        e = float((out[i, : ref.shape[0]].cpu() - ref).abs().max())
+        print(f"utt{i} (T={ref.shape[0]}) max abs err {e:.3e}")
+        assert e < TOL
 
 
 def test_transformer_enc_dec_speech2text_vs_reference_fixture():
@@ -69,7 +71,7 @@ def test_transformer_enc_dec_speech2text_vs_reference_fixture():
     wave = torch.from_numpy(z["wave"])
     speech, sl = s2t._to_batch([wave])
     enc, _ = s2t.asr_model.encode(speech, sl)
-    assert float((enc[0].cpu() - torch.from_numpy(z["enc"])).abs().max()) < 2e-3
+    assert float((enc[0].cpu() - torch.from_numpy(z["enc"])).abs().max()) < TOL
     assert s2t.ctc_greedy([wave])[0] == z["ctc_greedy"].tolist()
     for dn in DEC_NAMES:
         res = speech2text(cfg, w, nbest=10, **decode_params(z, dn))(z["wave"])

@@ -328,7 +328,8 @@ def test_search_on_very_short_utterances_host_logic(lens, beam, cw, mlr, minr, p
 
 def test_ctc_scoring_beyond_encoder_length_is_refused(monkeypatch):
     """maxlen > T + 1 with a CTC scorer: the reference dies with an IndexError inside ctc_prefix_score.py once the prefix outgrows the
-    encoder output; here it is refused up front (the device kernels would index their state out of bounds)."""
+    encoder output (only if a hypothesis is still alive then); here the kernels keep an all-logzero state instead of indexing out of bounds and
+    the search reports the utterance with the same exception type once it has really happened."""
     from espnet_b200.search import BatchBeamSearch
 
     emu_backend.install_search(monkeypatch)

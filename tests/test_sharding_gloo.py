@@ -54,6 +54,13 @@ def test_shard_and_gather_two_ranks():
         assert abs(score - (-float(i) - 0.5)) < 1e-6
 
 
+def test_empty_nbest_keeps_its_row():
+    """A real utterance whose search ended nothing (empty n-best) must not be confused with a padding row."""
+    rec = pack_hypotheses([[([3, 4], -1.0)], [], [([5], -2.0)]], nbest=2, max_tokens=4, rows=5)
+    out = unpack_hypotheses(rec, nbest=2)
+    assert len(out) == 3 and out[1] == [] and out[2][0][0] == [5] and out[0][0][0] == [3, 4]
+
+
 def test_shard_indices_cover_everything():
     for n in (1, 5, 8, 64):
         for world in (1, 2, 3, 8):

@@ -86,3 +86,20 @@ def test_end_of_search_log_lines(caplog):
     assert "total log probability: -3.25" in text and "normalized log probability: -0.54" in text
     assert "total number of ended hypotheses: 1" in text and "best hypo: ab<space>c" in text
     assert " -2.00 * 0.7 =  -1.40 for decoder" in text
+
+
+def test_speech2text_refuses_unimplemented_reference_keywords():
+    """lm_file / ngram_file / transducer_conf / streaming ... change the decoding algorithm: they must raise, not be swallowed (and they are
+    checked before any device work, so this runs without a GPU)."""
+    import pytest
+
+    import espnet_b200
+
+    for kw in (dict(lm_file="lm.pth"), dict(ngram_file="4gram.bin"), dict(transducer_conf={"search_type": "default"}), dict(streaming=True),
+               dict(quantize_asr_model=True)):
+        with pytest.raises(NotImplementedError, match=list(kw)[0]):
+            espnet_b200.Speech2Text(asr_model=object(), **kw)
+    # defaults of those keywords pass this check (the next failure is the missing CUDA device / library, not the keyword filter)
+    with pytest.raises(Exception) as e:
+        espnet_b200.Speech2Text(asr_model=None, asr_train_config=None, lm_file=None, streaming=False, quantize_modules=["Linear"], device="cpu")
+    assert "does not implement" not in str(e.value)
