@@ -28,7 +28,7 @@ bool pdl_enabled() {
 extern "C" {
 
 const char* espb_last_error(void) { return g_err; }
-int espb_abi_version(void) { return 2; }   // 2: token_major argument of the CTC prefix entry points, espb_transpose_tv_f32, espb_global_mvn_f32
+int espb_abi_version(void) { return 3; }   // 3: espb_flash_attn_f32 (fused encoder self-attention)
 
 int espb_device_sm(int* major, int* minor) {
   int dev = 0;

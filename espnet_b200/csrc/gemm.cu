@@ -13,82 +13,16 @@
 
 #include "common.cuh"
 #include "gemm.h"
+#include "tc_common.cuh"
 
 namespace {
+
+using namespace espb::tc;
 
 constexpr int BM = 128;
 constexpr int BK = 32;                  // 32 fp32 = 128 B = one swizzle row
 constexpr int A_TILE_BYTES = BM * 128;  // one plane
 constexpr int NUM_THREADS = 192;
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // try_wait with a suspend-time hint: the warp sleeps in hardware instead of spinning through the issue slots the epilogue warps need.
-  uint32_t done = 0;
-  for (int spin = 0; ; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(0x989680u)
-        : "memory");
-    if (done) break;
-    if (spin > (1 << 22)) __trap();  // watchdog: fail loudly instead of hanging the GPU
-  }
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-
-// K-major, 128B-swizzled operand tile: LBO field 1 (unused for swizzled K-major), SBO = 8 rows * 128 B,
-// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
-  uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-  return (uint64_t)lo | ((uint64_t)hi << 32);
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ------------------------------------------------------------------ shared epilogue
 struct EpiArgs {
@@ -279,20 +213,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // neighbouring n-tiles of the same m-tile, each fetches 1/MC of the A tile and multicasts it to all of them, so every CTA ingests
 // A/MC + B instead of A + B.  A stage is refilled only after all MC consumers released it (their tcgen05.commit arrives on the
 // empty barrier of every CTA of the cluster).
-__device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank_v();
-__device__ __forceinline__ void cluster_sync_all_v();
-
 template <int BN, int STAGES, int MC>
 __global__ void __cluster_dims__(1, MC, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32x3_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym, int axm, int aym) {
@@ -462,18 +382,6 @@ gemm_tf32x3_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // 1/SK of the k-blocks of the SAME output tile in their own TMEM; the partial tiles are then reduce-scattered through distributed
 // shared memory: CTA r finalises the 32-column chunks c with c % SK == r, adding the other CTAs' partials in ascending rank order
 // (fixed order -> deterministic) before the usual bias / activation / residual / hi-lo split epilogue.
-__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
-  float4 v;
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %4, %5;\n\t"
-      "ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [ra];\n\t}"
-      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-      : "r"(local_addr), "r"(rank)
-      : "memory");
-  return v;
-}
-
 template <int BN, int STAGES, int SK>
 __global__ void __cluster_dims__(1, 1, SK) __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32x3_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p) {
@@ -669,45 +577,6 @@ gemm_tf32x3_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 //   warps 2-9: epilogue; warp e owns TMEM lanes 32*(e%4).. and columns (e/4)*BN/2 ..
 constexpr int V2_THREADS = 320;
 constexpr int CHUNK_KB = 4;
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank_v() { return cluster_ctarank(); }
-__device__ __forceinline__ void cluster_sync_all_v() { cluster_sync_all(); }
-__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit_2sm(uint32_t bar) {  // arrive on the barrier at this offset in both CTAs
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void mma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// relaxed: the barrier only orders TMEM reads (already fenced by tcgen05.wait::ld / fence::before_thread_sync); a release fence here
-// would make every chunk hand-over wait for the epilogue's outstanding global stores.
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t target_rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(local_bar), "r"(target_rank)
-      : "memory");
-}
 
 // rel-pos band (EspbGemmDesc::band_t): a tile of rows [m0, m0+bm) x columns [n0, n0+bn) is needed iff it intersects
 // { (m, n) : T-1-m <= n <= 2T-2-m }.
@@ -1098,53 +967,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(EspbGemmDesc p) {
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-// 5-D fp32 tensor map, 128B swizzle, box = {32, box_rows, 1, 1, 1}. strides in elements for dims 1..4.
 int make_map(CUtensorMap* map, const float* base, const long long dims[5], const long long strides_el[4], int box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) { espb_set_error("cuTensorMapEncodeTiled entry point not available"); return ESPB_ERR_TMA; }
-  cuuint64_t gdim[5], gstr[4];
-  cuuint32_t box[5] = {BK, (cuuint32_t)box_rows, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
-  long long packed = 1;
-  for (int i = 0; i < 5; ++i) {
-    gdim[i] = (cuuint64_t)(dims[i] > 0 ? dims[i] : 1);
-  }
-  packed = (long long)gdim[0];
-  for (int i = 0; i < 4; ++i) {
-    long long s = strides_el[i];
-    if (s <= 0) s = ((packed + 3) / 4) * 4;  // unused / broadcast dim (size 1): any legal stride
-    if (s % 4 != 0) { espb_set_error("TMA stride not a multiple of 16 bytes"); return ESPB_ERR_TMA; }
-    gstr[i] = (cuuint64_t)s * 4ull;
-    packed = s * (long long)gdim[i + 1];
-  }
-  if (reinterpret_cast<uintptr_t>(base) & 15) { espb_set_error("TMA base not 16-byte aligned"); return ESPB_ERR_TMA; }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    char buf[256];
-    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) dims=[%lld,%lld,%lld,%lld,%lld] strides=[%lld,%lld,%lld,%lld]", (int)r,
-             dims[0], dims[1], dims[2], dims[3], dims[4], strides_el[0], strides_el[1], strides_el[2], strides_el[3]);
-    espb_set_error(buf);
-    return ESPB_ERR_TMA;
-  }
-  return ESPB_OK;
+  return espb_make_tensor_map(map, base, dims, strides_el, BK, box_rows, 1);
 }
 
 template <int BN, int STAGES>
@@ -1252,6 +1076,57 @@ bool splitk_enabled() {
 }
 
 }  // namespace
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn espb_get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 5-D fp32 tensor map, 128B swizzle, box = {32, box_rows, 1, 1, 1}. strides in elements for dims 1..4.
+int espb_make_tensor_map(CUtensorMap* map, const float* base, const long long dims[5], const long long strides_el[4], int box0, int box1,
+                         int swizzle128) {
+  EncodeTiledFn fn = espb_get_encode_fn();
+  if (!fn) { espb_set_error("cuTensorMapEncodeTiled entry point not available"); return ESPB_ERR_TMA; }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t box[5] = {(cuuint32_t)box0, (cuuint32_t)box1, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+  long long packed = 1;
+  for (int i = 0; i < 5; ++i) {
+    gdim[i] = (cuuint64_t)(dims[i] > 0 ? dims[i] : 1);
+  }
+  packed = (long long)gdim[0];
+  for (int i = 0; i < 4; ++i) {
+    long long s = strides_el[i];
+    if (s <= 0) s = ((packed + 3) / 4) * 4;  // unused / broadcast dim (size 1): any legal stride
+    if (s % 4 != 0) { espb_set_error("TMA stride not a multiple of 16 bytes"); return ESPB_ERR_TMA; }
+    gstr[i] = (cuuint64_t)s * 4ull;
+    packed = s * (long long)gdim[i + 1];
+  }
+  if (reinterpret_cast<uintptr_t>(base) & 15) { espb_set_error("TMA base not 16-byte aligned"); return ESPB_ERR_TMA; }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) dims=[%lld,%lld,%lld,%lld,%lld] strides=[%lld,%lld,%lld,%lld]", (int)r,
+             dims[0], dims[1], dims[2], dims[3], dims[4], strides_el[0], strides_el[1], strides_el[2], strides_el[3]);
+    espb_set_error(buf);
+    return ESPB_ERR_TMA;
+  }
+  return ESPB_OK;
+}
+
 
 int espb_gemm_tc_launch(const EspbGemmDesc& d, cudaStream_t stream, int version) {
   if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.nbx <= 0 || d.nby <= 0) { espb_set_error("gemm: bad shape"); return ESPB_ERR_ARG; }

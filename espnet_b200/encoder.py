@@ -258,9 +258,11 @@ class ConformerEncoder(torch.nn.Module):
         qkv = self._buf("qkv", (2, M, 3 * D))
         qu, qv = self._buf("qu", (2, M, D)), self._buf("qv", (2, M, D))
         vt = self._buf("vt", (2, B, H, dk, Tp))
-        ac = self._buf("ac", (B, H, T, Tp))
         bd = self._buf("bd", (B, H, T, Rp))
-        probs = self._buf("probs", (2, B, H, T, Tp))
+        fused = ops.use_flash_attn(dk)      # one tcgen05 kernel for q k^T + rel_shift + softmax + p v (csrc/attention.cu); else materialised
+        if not fused:
+            ac = self._buf("ac", (B, H, T, Tp))
+            probs = self._buf("probs", (2, B, H, T, Tp))
         ctx = self._buf("ctx", (2, M, D))
         y = self._buf("y", (M, 2 * D))
         cv = self._buf("cv", (2, M, D))
@@ -276,14 +278,17 @@ class ConformerEncoder(torch.nn.Module):
             call("espb_qu_qv_f32", ptr(qkv), M * 3 * D, M, D, ptr(w["pos_u"]), ptr(w["pos_v"]), ptr(qu), ptr(qv), M * D)
             call("espb_v_transpose_f32", ptr(qkv), M * 3 * D, B, T, D, H, ptr(lens32), ptr(vt), B * H * dk * Tp, Tp)
             _count(2)
-            gemm(T, T, dk, qu, M * D, D, qkv, M * 3 * D, 3 * D, ac, Tp, nbx=H, nby=B, sa=(dk, T * D), sb=(dk, T * 3 * D),
-                 sc=(T * Tp, H * T * Tp), b_off=D)
             gemm(T, R, dk, qv, M * D, D, p_all, R * L * D, L * D, bd, Rp, nbx=H, nby=B, sa=(dk, T * D), sb=(dk, 0),
                  sc=(T * Rp, H * T * Rp), b_off=li * D, band_t=T)   # rel_shift only ever reads bd[i][T-1-i .. 2T-2-i]
-            call("espb_relpos_softmax_f32", ptr(ac), ptr(bd), B, H, T, Tp, Rp, ptr(lens32), math.sqrt(dk), ptr(probs), B * H * T * Tp)
-            _count()
-            gemm(T, dk, T, probs, B * H * T * Tp, Tp, vt, B * H * dk * Tp, Tp, ctx, D, c_plane=M * D, split_out=True, nbx=H, nby=B,
-                 sa=(T * Tp, H * T * Tp), sb=(dk * Tp, H * dk * Tp), sc=(dk, T * D))
+            if fused:
+                ops.flash_attn(qu, 0, D, qkv, D, 3 * D, vt, Tp, bd, Rp, lens32, B, H, T, dk, ctx)
+            else:
+                gemm(T, T, dk, qu, M * D, D, qkv, M * 3 * D, 3 * D, ac, Tp, nbx=H, nby=B, sa=(dk, T * D), sb=(dk, T * 3 * D),
+                     sc=(T * Tp, H * T * Tp), b_off=D)
+                call("espb_relpos_softmax_f32", ptr(ac), ptr(bd), B, H, T, Tp, Rp, ptr(lens32), math.sqrt(dk), ptr(probs), B * H * T * Tp)
+                _count()
+                gemm(T, dk, T, probs, B * H * T * Tp, Tp, vt, B * H * dk * Tp, Tp, ctx, D, c_plane=M * D, split_out=True, nbx=H, nby=B,
+                     sa=(T * Tp, H * T * Tp), sb=(dk * Tp, H * dk * Tp), sc=(dk, T * D))
             linear(ctx, w["out_w"], x, bias=w["out_b"], residual=x)
             # convolution module (encoder_layer.py:152-158, convolution.py:56-79)
             layernorm(x, *w["norm_conv"], LN_EPS, out_split=xn)

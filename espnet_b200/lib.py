@@ -47,6 +47,7 @@ _SIGS = {
     "espb_v_transpose_f32": [P, L, I, I, I, I, P, P, L, I, P],
     "espb_relpos_softmax_f32": [P, P, I, I, I, I, I, P, F, P, L, P],
     "espb_masked_softmax_f32": [P, I, I, I, I, P, F, P, L, P],
+    "espb_flash_attn_f32": [P, L, L, L, P, L, L, L, P, L, I, P, I, P, I, I, I, I, P, L, L, P],
     "espb_glu_dwconv_bn_swish_f32": [P, I, I, I, P, P, P, I, P, P, P, L, P],
     "espb_zero_pad_rows_f32": [P, I, I, I, P, L, I, P],
     "espb_log_softmax_rows_f32": [P, L, L, I, P],
@@ -67,7 +68,7 @@ _SIGS = {
     "espb_count_active_i32": [P, I, P, P],
 }
 
-ABI_VERSION = 2   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
+ABI_VERSION = 3   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["espb_last_error", "espb_abi_version", "espb_device_sm", "espb_frontend_blocks"])
 
 

@@ -100,6 +100,32 @@ def linear(x_split, w_split, out, *, bias=None, act=ACT_NONE, residual=None, alp
                 R=residual, ldr=N, alpha=alpha, act=act, force=force)
 
 
+# Fused tcgen05 self-attention (csrc/attention.cu) for d_k = 64; ESPB_ATTN=materialized keeps the round-1 GEMM + softmax + GEMM sequence
+# (A/B measurements and the validator of the fused kernel).
+_ATTN_MODE = os.environ.get("ESPB_ATTN", "fused")
+
+
+def set_attn_mode(mode):
+    global _ATTN_MODE
+    assert mode in ("fused", "materialized")
+    _ATTN_MODE = mode
+
+
+def attn_mode():
+    return _ATTN_MODE
+
+
+def use_flash_attn(dk):
+    return _ATTN_MODE == "fused" and dk == 64 and _GEMM_MODE != "simt"
+
+
+def flash_attn(q_split, q_off, ldq, k_split, k_off, ldk, vt, Tp, bd, Rp, lens32, B, H, T, dk, out_split):
+    """out_split [2][B*T][H*dk] = softmax((q k^T + rel_shift(bd)) / sqrt(dk)) v per (utterance, head); bd None: plain attention."""
+    call("espb_flash_attn_f32", ptr(q_split), q_off, q_split[0].numel(), ldq, ptr(k_split), k_off, k_split[0].numel(), ldk, ptr(vt),
+         vt[0].numel(), Tp, ptr(bd), Rp, ptr(lens32), B, H, T, dk, ptr(out_split), out_split[0].numel(), H * dk)
+    _count()
+
+
 def layernorm(x, gamma, beta, eps, out_plain=None, out_split=None):
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
     plane = out_split[0].numel() if out_split is not None else 0

@@ -12,6 +12,7 @@ from typing import List, Optional, Tuple
 
 import torch
 
+from . import ops
 from .encoder import LN_EPS, _Conv2dSubsampling, _FFN
 from .errors import TooShortUttError
 from .lib import call, ptr
@@ -159,8 +160,10 @@ class TransformerEncoder(torch.nn.Module):
         hbuf = self._buf("h", (2, M, U))
         qkv = self._buf("qkv", (2, M, 3 * D))
         vt = self._buf("vt", (2, B, H, dk, Tp))
-        sc = self._buf("sc", (B, H, T, Tp))
-        probs = self._buf("probs", (2, B, H, T, Tp))
+        fused = ops.use_flash_attn(dk)      # one tcgen05 kernel for q k^T + masked softmax + p v (csrc/attention.cu)
+        if not fused:
+            sc = self._buf("sc", (B, H, T, Tp))
+            probs = self._buf("probs", (2, B, H, T, Tp))
         ctx = self._buf("ctx", (2, M, D))
         for w in pk["layers"]:
             # x += MHA(LN1(x))  (encoder_layer.py:91-110, attention.py:262-265)
@@ -168,12 +171,15 @@ class TransformerEncoder(torch.nn.Module):
             linear(xn, w["qkv_w"], qkv, bias=w["qkv_b"], split_out=True)
             call("espb_v_transpose_f32", ptr(qkv), M * 3 * D, B, T, D, H, ptr(lens32), ptr(vt), B * H * dk * Tp, Tp)
             _count()
-            gemm(T, T, dk, qkv, M * 3 * D, 3 * D, qkv, M * 3 * D, 3 * D, sc, Tp, nbx=H, nby=B, sa=(dk, T * 3 * D), sb=(dk, T * 3 * D),
-                 sc=(T * Tp, H * T * Tp), b_off=D)
-            call("espb_masked_softmax_f32", ptr(sc), B, H, T, Tp, ptr(lens32), math.sqrt(dk), ptr(probs), B * H * T * Tp)
-            _count()
-            gemm(T, dk, T, probs, B * H * T * Tp, Tp, vt, B * H * dk * Tp, Tp, ctx, D, c_plane=M * D, split_out=True, nbx=H, nby=B,
-                 sa=(T * Tp, H * T * Tp), sb=(dk * Tp, H * dk * Tp), sc=(dk, T * D))
+            if fused:
+                ops.flash_attn(qkv, 0, 3 * D, qkv, D, 3 * D, vt, Tp, None, 0, lens32, B, H, T, dk, ctx)
+            else:
+                gemm(T, T, dk, qkv, M * 3 * D, 3 * D, qkv, M * 3 * D, 3 * D, sc, Tp, nbx=H, nby=B, sa=(dk, T * 3 * D), sb=(dk, T * 3 * D),
+                     sc=(T * Tp, H * T * Tp), b_off=D)
+                call("espb_masked_softmax_f32", ptr(sc), B, H, T, Tp, ptr(lens32), math.sqrt(dk), ptr(probs), B * H * T * Tp)
+                _count()
+                gemm(T, dk, T, probs, B * H * T * Tp, Tp, vt, B * H * dk * Tp, Tp, ctx, D, c_plane=M * D, split_out=True, nbx=H, nby=B,
+                     sa=(T * Tp, H * T * Tp), sb=(dk * Tp, H * dk * Tp), sc=(dk, T * D))
             linear(ctx, w["out_w"], x, bias=w["out_b"], residual=x)
             # x += w_2(relu(w_1(LN2(x))))  (encoder_layer.py:112-124)
             layernorm(x, *w["n2"], LN_EPS, out_split=xn)

@@ -93,6 +93,14 @@ int espb_relpos_softmax_f32(const float* ac, const float* bd, int B, int H, int 
  * keys j < lens[b], 0 elsewhere; scores [B][H][T][Tp] -> probs hi/lo planes [B][H][T][Tp]. */
 int espb_masked_softmax_f32(const float* scores, int B, int H, int T, int Tp, const int* lens, float sqrt_dk, float* probs, long long probs_plane,
                             cudaStream_t stream);
+/* Fused self-attention for d_k = 64 on tcgen05 (attention.py:416-459 rel-pos, :153-265 plain; scores and probabilities never reach HBM):
+ * out[b,i,h,:] = softmax_j<len_b( (q[b,i,h,:] . k[b,j,h,:] + bd[b,h,i,T-1-i+j]) / sqrt(d_k) ) . v[b,j,h,:].
+ * q / k / out are split (hi/lo plane) tensors (first element at q + q_off / k + k_off) with row strides ldq / ldk / ldo, head h at columns h*64..; vt is the split V^T [B][H][64][Tp]
+ * written by espb_v_transpose_f32; bd is the UNSHIFTED (q + pos_bias_v) p^T product [B][H][T][Rp] (rel_shift is applied while loading) or NULL
+ * for absolute-position attention.  Replaces the q k^T GEMM + espb_relpos_softmax_f32 / espb_masked_softmax_f32 + p v GEMM sequence. */
+int espb_flash_attn_f32(const float* q, long long q_off, long long q_plane, long long ldq, const float* k, long long k_off, long long k_plane,
+                        long long ldk, const float* vt, long long vt_plane, int Tp, const float* bd, int Rp, const int* lens, int B, int H, int T,
+                        int dk, float* out, long long out_plane, long long ldo, cudaStream_t stream);
 /* GLU -> depthwise Conv1d(K, pad (K-1)/2) -> BatchNorm1d(eval, folded) -> Swish (conformer/convolution.py:56-79). */
 int espb_glu_dwconv_bn_swish_f32(const float* y, int B, int Tmax, int C, const int* lens, const float* dw_w, const float* dw_b, int K,
                                  const float* bn_a, const float* bn_b, float* out, long long out_plane, cudaStream_t stream);

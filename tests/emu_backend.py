@@ -148,6 +148,30 @@ def _masked_softmax(sc, B, H, T, Tp, lens, sqrt_dk, probs, plane):
     _softmax_rows(s, lens.long().repeat_interleave(H * T), Tp, probs, plane)
 
 
+def _flash_attn(q, q_off, q_plane, ldq, k, k_off, k_plane, ldk, vt, vt_plane, Tp, bd, Rp, lens, B, H, T, dk, out, out_plane, ldo):
+    """flash_attn_kernel: out[b,i,h] = softmax_{j<len}((q.k + bd[b,h,i,T-1-i+j]) / sqrt(dk)) v; rows i >= len of an utterance are padding
+    (zero for whole 256-row blocks beyond len, finite values otherwise -- compared only below len)."""
+    qf, kf, vf, of = _flat(q), _flat(k), _flat(vt), _flat(out)
+    bdv = _flat(bd)[: B * H * T * Rp].view(B, H, T, Rp) if bd is not None else None
+    c = torch.arange(dk)
+    for b in range(B):
+        n = int(lens[b])
+        rows = (b * T + torch.arange(T)).view(T, 1)
+        for h in range(H):
+            qo = q_off + rows * ldq + h * dk + c
+            Q = qf[qo] + qf[qo + q_plane]
+            ko = k_off + rows[:n] * ldk + h * dk + c
+            K = kf[ko] + kf[ko + k_plane]
+            vo = ((b * H + h) * dk + c.view(dk, 1)) * Tp + torch.arange(n).view(1, n)
+            V = (vf[vo] + vf[vo + vt_plane]).t()
+            S = Q @ K.t()
+            if bdv is not None:
+                i, j = torch.arange(T).view(T, 1), torch.arange(n).view(1, n)
+                S = S + bdv[b, h][i, T - 1 - i + j]
+            O = torch.softmax(S / math.sqrt(dk), dim=-1) @ V
+            _store(of, rows * ldo + h * dk + c, O, True, out_plane)
+
+
 def _glu_dwconv_bn_swish(y, B, Tmax, C, lens, dw_w, dw_b, K, bn_a, bn_b, out, out_plane):
     yv = _flat(y)[: B * Tmax * 2 * C].view(B, Tmax, 2 * C)
     t = torch.arange(Tmax).view(1, Tmax, 1)
@@ -162,7 +186,7 @@ def _glu_dwconv_bn_swish(y, B, Tmax, C, lens, dw_w, dw_b, K, bn_a, bn_b, out, ou
 
 _TABLE = {"espb_split_tf32_f32": _split_tf32, "espb_layernorm_f32": _layernorm, "espb_conv1_relu_f32": _conv1_relu, "espb_qu_qv_f32": _qu_qv,
           "espb_v_transpose_f32": _v_transpose, "espb_relpos_softmax_f32": _relpos_softmax, "espb_masked_softmax_f32": _masked_softmax,
-          "espb_glu_dwconv_bn_swish_f32": _glu_dwconv_bn_swish}
+          "espb_flash_attn_f32": _flash_attn, "espb_glu_dwconv_bn_swish_f32": _glu_dwconv_bn_swish}
 calls = []   # names of the emulated entry points, in call order (tests can assert on the sequence)
 
 

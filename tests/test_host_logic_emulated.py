@@ -414,3 +414,39 @@ def test_minlenratio_retry_is_per_utterance(monkeypatch):
     full = bs.forward_batch(enc, el, model.enc_split(enc), -2.0, 0.3)
     assert len(full[0]) > 0 and [h.yseq.tolist() for h in full[1]] == [h.yseq.tolist() for h in first[1]]
     assert all(len(h.yseq) == 4 for h in full[0])          # sos + 2 tokens + the eos appended at maxlen
+
+
+@pytest.mark.parametrize("kind", ["conformer", "transformer"])
+def test_fused_attention_call_host_logic(kind, monkeypatch):
+    """d_k = 64 takes the fused attention entry point (espb_flash_attn_f32: pointer / offset / stride arguments of q, k, V^T, bd and the
+    context buffer); ragged batch against the oracle, and the same numbers as the materialised sequence."""
+    import espnet_b200
+    from espnet_b200 import ops
+    from oracle import encoder as OE
+    from oracle import transformer_encoder as TE
+
+    emu_backend.install(monkeypatch)
+    torch.manual_seed(4)
+    if kind == "conformer":
+        enc = espnet_b200.ConformerEncoder(80, output_size=128, attention_heads=2, linear_units=64, num_blocks=2, input_layer="conv2d",
+                                           macaron_style=True, rel_pos_type="latest", pos_enc_layer_type="rel_pos",
+                                           selfattention_layer_type="rel_selfattn", cnn_module_kernel=7).eval()
+    else:
+        enc = espnet_b200.TransformerEncoder(80, output_size=128, attention_heads=2, linear_units=64, num_blocks=2).eval()
+    w = {"encoder." + k: v.detach().clone() for k, v in enc.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    lens = [70, 41]
+    feats = torch.zeros(2, 70, 80)
+    for i, n in enumerate(lens):
+        feats[i, :n] = torch.randn(n, 80, generator=g)
+    monkeypatch.setattr(ops, "_ATTN_MODE", "fused")
+    out, olens, _ = enc(feats, torch.tensor(lens))
+    assert emu_backend.calls.count("espb_flash_attn_f32") == 2 and "espb_relpos_softmax_f32" not in emu_backend.calls
+    monkeypatch.setattr(ops, "_ATTN_MODE", "materialized")
+    out2, _, _ = enc(feats, torch.tensor(lens))
+    for i, n in enumerate(lens):
+        ref = (OE.conformer_encode if kind == "conformer" else TE.transformer_encode)(feats[i, :n], w, 2, 2)
+        T = ref.shape[0]
+        assert int(olens[i]) == T
+        np.testing.assert_allclose(out[i, :T].numpy(), ref.numpy(), atol=5e-5, rtol=1e-5)
+        np.testing.assert_allclose(out[i, :T].numpy(), out2[i, :T].numpy(), atol=2e-5, rtol=1e-5)
