@@ -15,9 +15,10 @@
 // kernel.  The A operands (Q hi/lo, P hi/lo) live in TENSOR MEMORY, so the MMAs read only the B tiles from shared memory.
 //
 //   warp 0 (lane 0)      TMA producer: K tiles, V^T tiles (SWIZZLE_128B, cta_group::2 loads signalling the leader's barriers) and, for
-//                        rel-pos attention, per softmax warp a 32 x 96 window of the UNSHIFTED bd = (q+v) p^T matrix (rel_shift is a
-//                        row-dependent column offset: row i needs bd[i][T-1-i+j]; a 96-wide unswizzled row makes lane l's read of
-//                        column 31-l+jj bank-conflict free)
+//                        rel-pos attention, per softmax warp a 32 x 100 window of the UNSHIFTED bd = (q+v) p^T matrix (rel_shift is a
+//                        row-dependent column offset: row i needs bd[i][T-1-i+j]; TMA needs a 16-byte aligned start column, so the box
+//                        starts at the window start rounded down to a multiple of 4 -- the remainder T mod 4 is the same for every
+//                        window; an odd multiple of 4 floats as the unswizzled row pitch makes lane l's reads bank-conflict free)
 //   warp 1 (lane 0, leader CTA)  MMA issue: S(t) = Q K(t)^T into S[t&1]; after P(t) is published: O(t) = P(t) V(t) into O[t&1]; S(t+2)
 //   warps 2-5            softmax: thread = query row.  S(t) from TMEM, + bd window from smem, scale, mask, running max / sum, P(t) hi/lo
 //                        back to TMEM; O(t-1) from TMEM folded into the fp32 register accumulator with the rescale factor.
@@ -41,7 +42,7 @@ constexpr int KV_STAGES = 3;
 constexpr int BD_STAGES = 2;
 constexpr int TILE_BYTES = 32 * 128;        // one [32 rows x 32 fp32] swizzled operand block
 constexpr int KV_STAGE_BYTES = 4 * TILE_BYTES;          // [hi | lo] x [k-block 0 | 1]
-constexpr int BD_COLS = 96;
+constexpr int BD_COLS = 100;                 // 32 + 64 - 1 window columns + up to 3 columns of alignment slack, a multiple of 4
 constexpr int BD_WARP_BYTES = 32 * BD_COLS * 4;
 constexpr int BD_STAGE_BYTES = 4 * BD_WARP_BYTES;
 constexpr int ATT_THREADS = 192;
@@ -138,13 +139,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
           tma_load_5d_2sm(dst + 2 * TILE_BYTES, &tmK, fb, 0, row, h, b, 1);
           tma_load_5d_2sm(dst + 3 * TILE_BYTES, &tmK, fb, 32, row, h, b, 1);
         }
-        if (RELPOS) {  // bd windows: warp quarter q gets rows R0+32q.. and columns c0 = T-1-(row0+31)+J0 .. c0+95 (out-of-range -> zero fill)
+        if (RELPOS) {  // bd windows: warp quarter q gets rows R0+32q.. and columns c0 = T-1-(row0+31)+J0 - (T&3) .. +99 (out-of-range -> zero fill)
           const int sb = t % BD_STAGES;
           mbar_wait(bd_empty + 8 * sb, (uint32_t)(((t / BD_STAGES) & 1) ^ 1));
           mbar_expect_tx(bd_full + 8 * sb, BD_STAGE_BYTES);
           for (int q = 0; q < 4; ++q) {
             const int row0 = R0 + 32 * q;
-            tma_load_5d(bd_base + sb * BD_STAGE_BYTES + q * BD_WARP_BYTES, &tmBD, bd_full + 8 * sb, p.T - 1 - (row0 + 31) + J0, row0, h, b, 0);
+            tma_load_5d(bd_base + sb * BD_STAGE_BYTES + q * BD_WARP_BYTES, &tmBD, bd_full + 8 * sb, p.T - 1 - (row0 + 31) + J0 - (p.T & 3), row0, h, b, 0);
           }
         }
         {  // V^T tile: this CTA's 32 d_k rows x 64 keys
@@ -239,8 +240,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
     for (int j = 0; j < DK; ++j) o_acc[j] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
     const float scale = p.scale;
-    // this lane's window of the bd tile: row `lane` of the warp's [32][96] block, starting at column 31 - lane (bank = (31 - lane + j) mod 32)
-    const float* bd_lane = reinterpret_cast<const float*>(smem_al + (bd_base - smem_base) + q * BD_WARP_BYTES) + lane * BD_COLS + (31 - lane);
+    // this lane's window of the bd tile: row `lane` of the warp's [32][100] block, starting at column 31 - lane + (T & 3)
+    // (bank = (3 * lane + const + j) mod 32: distinct over the warp)
+    const float* bd_lane = reinterpret_cast<const float*>(smem_al + (bd_base - smem_base) + q * BD_WARP_BYTES) + lane * BD_COLS + (31 - lane) + (p.T & 3);
 
     for (int t = 0; t < nkt; ++t) {
       const int J0 = t * KB;
