@@ -3,12 +3,13 @@
 Public surface mirrors the reference classes on that path:
 Speech2Text, ESPnetASRModel, DefaultFrontend, UtteranceMVN, ConformerEncoder, CTC,
 TransformerDecoder, BatchBeamSearch, Hypothesis, TooShortUttError (+ GlobalMVN, the output-side text classes, and the
-TransformerEncoder of the next scope row, whose CUDA path is still opt-in in the tests).
+TransformerEncoder of the next scope row; CTCPrefixScorer and TransformerDecoder.batch_score implement the reference's scorer protocol,
+``espnet_b200.integration.register()`` adds the classes to the reference's registries).
 All compute goes through the C-ABI CUDA library ``libespnet_b200.so`` (include/espnet_b200.h).
 """
 from .asr_inference import (ESPnetASRModel, Speech2Text, build_model, build_model_from_file, decoder_choices,  # noqa: F401
                             encoder_choices, frontend_choices, normalize_choices)
-from .ctc import CTC  # noqa: F401
+from .ctc import CTC, CTCPrefixScorer  # noqa: F401
 from .decoder import TransformerDecoder  # noqa: F401
 from .encoder import ConformerEncoder  # noqa: F401
 from .errors import TooShortUttError  # noqa: F401

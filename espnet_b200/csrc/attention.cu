@@ -36,6 +36,12 @@ namespace {
 
 using namespace espb::tc;
 
+#ifdef ESPB_ATTN_SLEEP_WAIT
+#define ATT_WAIT mbar_wait
+#else
+#define ATT_WAIT mbar_wait_spin
+#endif
+
 constexpr int DK = 64;                      // head dimension served by this kernel
 constexpr int KB = 64;                      // keys per tile
 constexpr int KV_STAGES = 3;
@@ -129,7 +135,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
         const uint32_t ph = (uint32_t)((t / KV_STAGES) & 1);
         const int J0 = t * KB;
         {  // K tile: this CTA's 32 keys x 64 d_k, hi/lo planes, two 32-wide k-blocks
-          mbar_wait(k_empty + 8 * s, ph ^ 1);
+          ATT_WAIT(k_empty + 8 * s, ph ^ 1);
           if (leader) mbar_expect_tx(k_full + 8 * s, 2 * KV_STAGE_BYTES);
           const uint32_t fb = (k_full & 0xFEFFFFFFu) + 8 * s;       // the leader CTA's barrier
           const uint32_t dst = k_base + s * KV_STAGE_BYTES;
@@ -141,7 +147,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
         }
         if (RELPOS) {  // bd windows: warp quarter q gets rows R0+32q.. and columns c0 = T-1-(row0+31)+J0 - (T&3) .. +99 (out-of-range -> zero fill)
           const int sb = t % BD_STAGES;
-          mbar_wait(bd_empty + 8 * sb, (uint32_t)(((t / BD_STAGES) & 1) ^ 1));
+          ATT_WAIT(bd_empty + 8 * sb, (uint32_t)(((t / BD_STAGES) & 1) ^ 1));
           mbar_expect_tx(bd_full + 8 * sb, BD_STAGE_BYTES);
           for (int q = 0; q < 4; ++q) {
             const int row0 = R0 + 32 * q;
@@ -149,7 +155,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
           }
         }
         {  // V^T tile: this CTA's 32 d_k rows x 64 keys
-          mbar_wait(v_empty + 8 * s, ph ^ 1);
+          ATT_WAIT(v_empty + 8 * s, ph ^ 1);
           if (leader) mbar_expect_tx(v_full + 8 * s, 2 * KV_STAGE_BYTES);
           const uint32_t fb = (v_full & 0xFEFFFFFFu) + 8 * s;
           const uint32_t dst = v_base + s * KV_STAGE_BYTES;
@@ -168,7 +174,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       auto issue_s = [&](int t) {
         const int s = t % KV_STAGES;
-        mbar_wait(k_full + 8 * s, (uint32_t)((t / KV_STAGES) & 1));
+        ATT_WAIT(k_full + 8 * s, (uint32_t)((t / KV_STAGES) & 1));
         tcgen05_fence_after();
         const uint32_t kb_smem = k_base + s * KV_STAGE_BYTES;
         const uint32_t d = tmem_base + TM_S + (uint32_t)(t & 1) * 64;
@@ -184,14 +190,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
         tcgen05_commit_2sm(k_empty + 8 * s);
         tcgen05_commit_2sm(s_full + 8 * (t & 1));
       };
-      mbar_wait(q_full, 0);
+      ATT_WAIT(q_full, 0);
       tcgen05_fence_after();
       issue_s(0);
       if (nkt > 1) issue_s(1);
       for (int t = 0; t < nkt; ++t) {
         const int s = t % KV_STAGES;
-        mbar_wait(p_full, (uint32_t)(t & 1));        // P(t) is in TMEM in both CTAs; S(t) and O(t-2) have been consumed
-        mbar_wait(v_full + 8 * s, (uint32_t)((t / KV_STAGES) & 1));
+        ATT_WAIT(p_full, (uint32_t)(t & 1));        // P(t) is in TMEM in both CTAs; S(t) and O(t-2) have been consumed
+        ATT_WAIT(v_full + 8 * s, (uint32_t)((t / KV_STAGES) & 1));
         tcgen05_fence_after();
         const uint32_t vb_smem = v_base + s * KV_STAGE_BYTES;
         const uint32_t d = tmem_base + TM_O + (uint32_t)(t & 1) * 64;
@@ -247,14 +253,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
     for (int t = 0; t < nkt; ++t) {
       const int J0 = t * KB;
       float s[KB];
-      mbar_wait(s_full + 8 * (t & 1), (uint32_t)((t >> 1) & 1));
+      ATT_WAIT(s_full + 8 * (t & 1), (uint32_t)((t >> 1) & 1));
       tcgen05_fence_after();
       tmem_ld32_nowait(tmem_base + tlane + TM_S + (uint32_t)(t & 1) * 64, s);
       tmem_ld32_nowait(tmem_base + tlane + TM_S + (uint32_t)(t & 1) * 64 + 32, s + 32);
       tmem_ld_wait();
       if (RELPOS) {
         const int sb = t % BD_STAGES;
-        mbar_wait(bd_full + 8 * sb, (uint32_t)((t / BD_STAGES) & 1));
+        ATT_WAIT(bd_full + 8 * sb, (uint32_t)((t / BD_STAGES) & 1));
         const float* a = bd_lane + sb * (BD_STAGE_BYTES / 4);
 #pragma unroll
         for (int j = 0; j < KB; ++j) s[j] += a[j];
@@ -279,7 +285,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
       l_run = fmaf(l_run, alpha, lsum);
       m_run = m_new;
       if (t > 0) {   // O(t-1) is complete (and P(t-1) has been read): fold it in with the rescale of step t-1
-        mbar_wait(o_full + 8 * ((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1));
+        ATT_WAIT(o_full + 8 * ((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1));
         tcgen05_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -310,7 +316,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
     }
     {  // last tile's O, normalise, store hi/lo
       const int t = nkt - 1;
-      mbar_wait(o_full + 8 * (t & 1), (uint32_t)((t >> 1) & 1));
+      ATT_WAIT(o_full + 8 * (t & 1), (uint32_t)((t >> 1) & 1));
       tcgen05_fence_after();
       const float inv = 1.f / l_run;
       float* o = p.out + ((long long)b * p.T + row) * p.ldo + h * DK;

@@ -30,6 +30,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1 << 22)) __trap();  // watchdog: fail loudly instead of hanging the GPU
   }
 }
+// Latency-critical waits (the consumer is idle until the barrier flips and sits on the critical path): plain try_wait polling without a
+// suspend-time hint.  Measured on the fused attention kernel (ncu source view): with the 10 ms hint a waiter that misses its first probe
+// resumes ~1000+ cycles after the phase completes.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; ; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (spin > (1u << 26)) __trap();  // watchdog
+  }
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(

@@ -119,6 +119,65 @@ class TransformerDecoder(torch.nn.Module):
             self.buf_version = getattr(self, "buf_version", 0) + 1   # captured CUDA graphs hold these pointers
         return t
 
+    # ---------------------------------------------------------------- BatchScorerInterface (espnet2/legacy/nets/scorer_interface.py:85-188)
+    # The functional scorer protocol of the reference's (Batch)BeamSearch: states are opaque objects the search threads through
+    # select_state / batch_score, so the reference's own search can drive this decoder.  A hypothesis' state is (k, v): the
+    # self-attention K / V rows of its prefix for every layer, each [L][len][D] (the reference keeps the layer OUTPUTS of the
+    # prefix, transformer_decoder.py:262-311, and re-projects them every step).  Each call copies the states into the position-major
+    # cache and runs the same kernels as the device-resident search (`step`); espnet_b200.BatchBeamSearch does not go through here.
+    def init_state(self, x: torch.Tensor):
+        return None
+
+    def batch_init_state(self, x: torch.Tensor):
+        return self.init_state(x)
+
+    def select_state(self, state, i: int, new_id: int = None):
+        return None if state is None else state[i]
+
+    def final_score(self, state) -> float:
+        return 0.0
+
+    def _iface_memory(self, x, n, need_len):
+        """Cross-attention K / V of the utterance whose encoder output is x (T, D): projected once and kept while x is the same tensor."""
+        key = (x.data_ptr(), tuple(x.shape), x._version)
+        c = getattr(self, "_iface", None)
+        if c is None or c["key"] != key:
+            T = x.shape[0]
+            self.ws_tag = "iface"
+            c = self._iface = dict(key=key, enc_split=split_from(x.contiguous().float()), lens32=torch.tensor([T], dtype=torch.int32, device=x.device),
+                                   T=T, st=None)
+        st = c["st"]
+        if st is None or st["n"] != n or st["max_len"] < need_len:
+            cap = max(32, 1 << (need_len - 1).bit_length())
+            self.ws_tag = "iface"
+            c["st"] = st = self.init_memory(c["enc_split"], 1, c["T"], c["lens32"], n, cap)
+        return st
+
+    @torch.no_grad()
+    def batch_score(self, ys: torch.Tensor, states, xs: torch.Tensor):
+        """ys (n, len) int64 prefixes (with sos), states: list of n per-hypothesis states (None at the first step), xs (n, T, D) the
+        encoder output repeated per hypothesis -> (log-probabilities (n, V), list of n new states).  transformer_decoder.py:262-311."""
+        n, ln = ys.shape
+        pos = ln - 1
+        st = self._iface_memory(xs[0], n, ln)
+        self.ws_tag = "iface"
+        L, D = self.num_blocks, self.d
+        kc, vc = st["kc"], st["vc"]                          # [L][max_len][n][D]
+        if pos > 0:
+            kc[:, :pos] = torch.stack([s[0] for s in states], dim=2)
+            vc[:, :pos] = torch.stack([s[1] for s in states], dim=2)
+        anc = self._buf("iface_anc", (n, st["max_len"] + 1), dtype=torch.int32)
+        anc.copy_(torch.arange(n, dtype=torch.int32, device=anc.device).view(n, 1).expand_as(anc))   # every slot is its own ancestor
+        logp = self.step(st, pos, ys[:, -1].to(torch.int32).contiguous(), anc, n, None)
+        new_states = [(kc[:, :ln, b].clone(), vc[:, :ln, b].clone()) for b in range(n)]
+        return logp.clone(), new_states
+
+    @torch.no_grad()
+    def score(self, ys: torch.Tensor, state, x: torch.Tensor):
+        """ScorerInterface.score for one hypothesis (transformer_decoder.py:240-260)."""
+        logp, states = self.batch_score(ys.unsqueeze(0), [state], x.unsqueeze(0))
+        return logp[0], states[0]
+
     # ---------------------------------------------------------------- device-side incremental scorer
     @torch.no_grad()
     def init_memory(self, enc_split, U, Tmax, lens32, n_slots, max_len):

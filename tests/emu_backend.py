@@ -360,7 +360,7 @@ def _ctc_score_dense(logp, U, Tmax, V, lens, blank, eos, W, r_prev, s_prev, last
 def _ctc_advance(logp, U, Tmax, V, lens, blank, eos, W, r_prev, parent, par_last_tok, new_tok, new_active, out_len, step_ptr, r_new, s_new,
                  token_major):
     out_len += _step(step_ptr)
-    rp, ro = r_prev.view(U * W, Tmax, 4), r_new.view(U * W, Tmax, 4)
+    rp, ro = r_prev.view(-1, Tmax, 4), r_new.view(U * W, Tmax, 4)      # parents may come from a larger set of previous slots (scorer protocol)
     Z4 = torch.tensor([LOGZERO, LOGZERO, _lae(LOGZERO, LOGZERO), 0.0])
     for s in range(U * W):
         u, c, act = s // W, int(new_tok.view(-1)[s]), int(new_active.view(-1)[s])
