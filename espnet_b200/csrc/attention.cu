@@ -128,8 +128,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer (one lane per CTA)
-    if (lane == 0) {
+    // ===================================================================== TMA producer (one elected lane per CTA)
+    if (elect_one_sync()) {
       for (int t = 0; t < nkt; ++t) {
         const int s = t % KV_STAGES;
         const uint32_t ph = (uint32_t)((t / KV_STAGES) & 1);
@@ -168,8 +168,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (leader CTA, one lane)
-    if (leader && lane == 0) {
+    // ===================================================================== MMA issuer (leader CTA, one elected lane)
+    if (leader && elect_one_sync()) {
       // D = f32, A = B = tf32, K-major, N = 64, M = 256 (cta_group::2)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       auto issue_s = [&](int t) {

@@ -79,7 +79,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   espb::pdl_wait();      // first global access (TMA loads of A / B) follows
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {   // one lane, known to ptxas: uniform-datapath issue without per-instruction waterfall loops
       const int cblk = (p.a_mode == 1) ? p.cv_cin / BK : 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
@@ -105,7 +105,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {   // one lane, known to ptxas: uniform-datapath issue without per-instruction waterfall loops
       // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2 at bits 7,10), both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -252,7 +252,7 @@ gemm_tf32x3_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   espb::pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {   // one lane, known to ptxas: uniform-datapath issue without per-instruction waterfall loops
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -272,7 +272,7 @@ gemm_tf32x3_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {   // one lane, known to ptxas: uniform-datapath issue without per-instruction waterfall loops
       // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2 at bits 7,10), both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -425,7 +425,7 @@ gemm_tf32x3_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t stg_lane = smem_base + (uint32_t)(q * 32 + lane) * 16u;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {   // one lane, known to ptxas: uniform-datapath issue without per-instruction waterfall loops
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
@@ -441,7 +441,7 @@ gemm_tf32x3_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {   // one lane, known to ptxas: uniform-datapath issue without per-instruction waterfall loops
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
@@ -641,7 +641,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {   // one lane, known to ptxas: uniform-datapath issue without per-instruction waterfall loops
       const int cblk = (p.a_mode == 1) ? p.cv_cin / BK : 0;
       const uint32_t leader_full = full_bar & 0xFEFFFFFFu;   // same offset in the even (leader) CTA of the pair
       long long g = 0;                                        // global k-block counter (stage ring position)
@@ -677,7 +677,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader && elect_one_sync()) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       long long g = 0, cg = 0;                                // global k-block / chunk counters
       for (long long tile = pair; tile < total_tiles; tile += num_pairs) {

@@ -205,6 +205,20 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of a converged warp.  Unlike `lane == 0`, ptxas knows that exactly one thread runs the guarded region, so the operands of the
+// warp-uniform instructions inside (UTCHMMA, UTMALDG, UTCBAR: uniform-register operands) need no per-instruction ELECT / BRA.U.ANY
+// "waterfall" loop (measured: ~58 -> issue-limited cycles per tcgen05.mma in the fused attention kernel).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }

@@ -127,7 +127,7 @@ class CTCPrefixScorer:
     @torch.no_grad()
     def batch_score_partial(self, y: torch.Tensor, ids: torch.Tensor, state, x: torch.Tensor):
         """y (n, len) int64 prefixes, ids (n, k) int64 tokens to score, state: list of n hypothesis states (None before the first step)."""
-        n, k = ids.shape
+        n = y.shape[0]
         dev = y.device
         out_len = y.shape[1] - 1
         if state is None or state[0] is None:
@@ -137,6 +137,13 @@ class CTCPrefixScorer:
             r_prev = torch.stack([s.r for s in state]).contiguous()
             s_prev = torch.stack([s.s for s in state]).contiguous()
         last_tok = y[:, -1].to(torch.int32).contiguous()
+        if ids is None:     # no pre-beam (CTC-only decoding): every token is scored (ctc_prefix_score.py:118-122)
+            scores = torch.empty(n, self.V, dtype=torch.float32, device=dev)
+            call("espb_ctc_score_dense_f32", ptr(self.logp), 1, self.T, self.V, ptr(self.lens32), self.blank, self.eos, n, ptr(r_prev), ptr(s_prev),
+                 ptr(last_tok), out_len, ptr(scores))
+            _count()
+            return scores, _CTCBatchState(r_prev, last_tok, out_len)
+        k = ids.shape[1]
         cand = ids.to(torch.int32).contiguous()
         part = torch.empty(n, k + 1, dtype=torch.float32, device=dev)
         psi = torch.empty(n, k + 1, dtype=torch.float32, device=dev)

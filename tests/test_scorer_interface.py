@@ -65,7 +65,7 @@ def _drive(model, z, dn, device):
     _check(hyps[:10], decode_results(z, dn))
 
 
-@pytest.mark.parametrize("dn", ["joint", "att", "joint_pen"])
+@pytest.mark.parametrize("dn", ["joint", "att", "ctc", "joint_pen"])
 def test_reference_beam_search_drives_our_scorers_host_logic(dn, monkeypatch):
     import argparse
 
