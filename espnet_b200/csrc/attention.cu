@@ -19,9 +19,11 @@
 //                        row-dependent column offset: row i needs bd[i][T-1-i+j]; TMA needs a 16-byte aligned start column, so the box
 //                        starts at the window start rounded down to a multiple of 4 -- the remainder T mod 4 is the same for every
 //                        window; an odd multiple of 4 floats as the unswizzled row pitch makes lane l's reads bank-conflict free)
-//   warp 1 (lane 0, leader CTA)  MMA issue: S(t) = Q K(t)^T into S[t&1]; after P(t) is published: O(t) = P(t) V(t) into O[t&1]; S(t+2)
-//   warps 2-5            softmax: thread = query row.  S(t) from TMEM, + bd window from smem, scale, mask, running max / sum, P(t) hi/lo
-//                        back to TMEM; O(t-1) from TMEM folded into the fp32 register accumulator with the rescale factor.
+//   warp 1 (lane 0, leader CTA)  MMA issue: S(t) = Q K(t)^T into S[t&1] as soon as S(t-2) has been read; after P(t) is published:
+//                        O(t) = P(t) V(t) into O[t&1]
+//   warps 2-9            softmax, two warpgroups: thread = (query row, 32-column half).  S(t) from TMEM, + bd window from smem, scale, mask,
+//                        running max (exchanged between the halves through smem) / sum, P(t) hi/lo back to TMEM; O(t-1) from TMEM folded
+//                        into the fp32 register accumulator with the rescale factor.
 //
 // TMEM columns (512): Q hi 0-63 | Q lo 64-127 | S[0] 128-191 | S[1] 192-255 | P hi 256-319 | P lo 320-383 | O[0] 384-447 | O[1] 448-511.
 #include <cuda.h>
@@ -51,7 +53,7 @@ constexpr int KV_STAGE_BYTES = 4 * TILE_BYTES;          // [hi | lo] x [k-block 
 constexpr int BD_COLS = 100;                 // 32 + 64 - 1 window columns + up to 3 columns of alignment slack, a multiple of 4
 constexpr int BD_WARP_BYTES = 32 * BD_COLS * 4;
 constexpr int BD_STAGE_BYTES = 4 * BD_WARP_BYTES;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;                // warp 0: TMA, warp 1: MMA, warps 2-9: two softmax warpgroups
 constexpr uint32_t TM_QHI = 0, TM_QLO = 64, TM_S = 128, TM_PHI = 256, TM_PLO = 320, TM_O = 384;
 
 struct AttnParams {
@@ -74,9 +76,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
   const uint32_t bar_base = bd_base + (RELPOS ? BD_STAGES * BD_STAGE_BYTES : 0);
   const uint32_t k_full = bar_base, k_empty = k_full + 8 * KV_STAGES, v_full = k_empty + 8 * KV_STAGES, v_empty = v_full + 8 * KV_STAGES;
   const uint32_t bd_full = v_empty + 8 * KV_STAGES, bd_empty = bd_full + 8 * BD_STAGES;
-  const uint32_t s_full = bd_empty + 8 * BD_STAGES, o_full = s_full + 16, p_full = o_full + 16, q_full = p_full + 8;
+  const uint32_t s_full = bd_empty + 8 * BD_STAGES, o_full = s_full + 16, p_full = o_full + 16, q_full = p_full + 8, s_empty = q_full + 8;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + (q_full + 8 - smem_base));
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_al + (s_empty + 16 - smem_base));
+  const uint32_t xch_base = s_empty + 32;        // row-maximum exchange between the two softmax warpgroups: [2][2][128] floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -93,8 +96,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
     if (warp >= 2) {
       const int row = R0 + (warp & 3) * 32 + lane;
       if (row < p.T) {
-        float* o = p.out + ((long long)b * p.T + row) * p.ldo + h * DK;
-        for (int c = 0; c < DK; c += 4) {
+        float* o = p.out + ((long long)b * p.T + row) * p.ldo + h * DK + ((warp - 2) >> 2) * 32;
+        for (int c = 0; c < 32; c += 4) {
           *reinterpret_cast<float4*>(o + c) = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(o + p.out_plane + c) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -108,10 +111,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
       mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1);
       mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1);
     }
-    for (int s = 0; s < BD_STAGES; ++s) { mbar_init(bd_full + 8 * s, 1); mbar_init(bd_empty + 8 * s, 4); }
+    for (int s = 0; s < BD_STAGES; ++s) { mbar_init(bd_full + 8 * s, 1); mbar_init(bd_empty + 8 * s, 8); }
     for (int s = 0; s < 2; ++s) { mbar_init(s_full + 8 * s, 1); mbar_init(o_full + 8 * s, 1); }
-    mbar_init(p_full, 8);      // 4 softmax warps x 2 CTAs
-    mbar_init(q_full, 8);
+    mbar_init(p_full, 16);     // 8 softmax warps x 2 CTAs
+    mbar_init(q_full, 16);
+    mbar_init(s_empty, 16); mbar_init(s_empty + 8, 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
@@ -196,7 +200,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
       if (nkt > 1) issue_s(1);
       for (int t = 0; t < nkt; ++t) {
         const int s = t % KV_STAGES;
-        ATT_WAIT(p_full, (uint32_t)(t & 1));        // P(t) is in TMEM in both CTAs; S(t) and O(t-2) have been consumed
+        if (t + 2 < nkt) {   // S(t) is in the softmax threads' registers: its buffer takes S(t+2), which then runs under softmax(t) instead of
+          ATT_WAIT(s_empty + 8 * (t & 1), (uint32_t)((t >> 1) & 1));   // queueing between P V(t) and P V(t+1) on the in-order tensor pipe
+          tcgen05_fence_after();
+          issue_s(t + 2);
+        }
+        ATT_WAIT(p_full, (uint32_t)(t & 1));        // P(t) is in TMEM in both CTAs; O(t-2) has been consumed
         ATT_WAIT(v_full + 8 * s, (uint32_t)((t / KV_STAGES) & 1));
         tcgen05_fence_after();
         const uint32_t vb_smem = v_base + s * KV_STAGE_BYTES;
@@ -212,73 +221,83 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
         }
         tcgen05_commit_2sm(v_empty + 8 * s);
         tcgen05_commit_2sm(o_full + 8 * (t & 1));
-        if (t + 2 < nkt) issue_s(t + 2);
       }
     }
   } else {
-    // ===================================================================== softmax / accumulate: thread = query row
+    // ===================================================================== softmax / accumulate: two warpgroups, thread = (query row, half)
+    // Warps w and w + 4 own the same TMEM lane quarter (rows); group g = 0 / 1 handles key columns [32g, 32g+32) of every S tile and
+    // output columns [32g, 32g+32) of O.  The two threads of a row agree on the running maximum through shared memory (one 64-thread
+    // named barrier per tile); their partial row sums are only combined at the end (same maxima -> the partial sums simply add).
     const int q = warp & 3;                                   // TMEM lane quarter of this warp
+    const int g = (warp - 2) >> 2;                            // column half
     const uint32_t tlane = ((uint32_t)(q * 32)) << 16;
-    const int row = R0 + q * 32 + lane;
-    {  // Q hi/lo of this row -> TMEM (rows >= T: zeros)
-      const float* qp = p.q + ((long long)b * p.T + row) * p.ldq + h * DK;
+    const int rloc = q * 32 + lane;                           // row within the CTA
+    const int row = R0 + rloc;
+    const uint32_t cg = (uint32_t)g * 32;
+    float* xch = reinterpret_cast<float*>(smem_al + (xch_base - smem_base));    // [2 parities][2 groups][128 rows]
+    {  // Q hi/lo of this row, columns [32g, 32g+32) -> TMEM (rows >= T: zeros)
+      const float* qp = p.q + ((long long)b * p.T + row) * p.ldq + h * DK + cg;
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl) {
+        float v[32];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < p.T) x = __ldg(reinterpret_cast<const float4*>(qp + pl * p.q_plane + c * 32 + j));
-            v[j] = x.x; v[j + 1] = x.y; v[j + 2] = x.z; v[j + 3] = x.w;
-          }
-          tmem_st32(tmem_base + tlane + (pl ? TM_QLO : TM_QHI) + c * 32, v);
+        for (int j = 0; j < 32; j += 4) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < p.T) x = __ldg(reinterpret_cast<const float4*>(qp + pl * p.q_plane + j));
+          v[j] = x.x; v[j + 1] = x.y; v[j + 2] = x.z; v[j + 3] = x.w;
         }
+        tmem_st32(tmem_base + tlane + (pl ? TM_QLO : TM_QHI) + cg, v);
       }
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(q_full, 0);
     }
-    float o_acc[DK];
+    float o_acc[32];
 #pragma unroll
-    for (int j = 0; j < DK; ++j) o_acc[j] = 0.f;
+    for (int j = 0; j < 32; ++j) o_acc[j] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
     const float scale = p.scale;
-    // this lane's window of the bd tile: row `lane` of the warp's [32][100] block, starting at column 31 - lane + (T & 3)
+    // this lane's window of the bd tile: row `lane` of the quarter's [32][100] block, starting at column 31 - lane + (T & 3) + 32g
     // (bank = (3 * lane + const + j) mod 32: distinct over the warp)
-    const float* bd_lane = reinterpret_cast<const float*>(smem_al + (bd_base - smem_base) + q * BD_WARP_BYTES) + lane * BD_COLS + (31 - lane) + (p.T & 3);
+    const float* bd_lane = reinterpret_cast<const float*>(smem_al + (bd_base - smem_base) + q * BD_WARP_BYTES) + lane * BD_COLS + (31 - lane) + (p.T & 3) + cg;
 
     for (int t = 0; t < nkt; ++t) {
-      const int J0 = t * KB;
-      float s[KB];
+      const int J0 = t * KB + (int)cg;                        // first key of this thread's 32 columns
+      float s[32];
       ATT_WAIT(s_full + 8 * (t & 1), (uint32_t)((t >> 1) & 1));
       tcgen05_fence_after();
-      tmem_ld32_nowait(tmem_base + tlane + TM_S + (uint32_t)(t & 1) * 64, s);
-      tmem_ld32_nowait(tmem_base + tlane + TM_S + (uint32_t)(t & 1) * 64 + 32, s + 32);
+      tmem_ld32_nowait(tmem_base + tlane + TM_S + (uint32_t)(t & 1) * 64 + cg, s);
       tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(s_empty + 8 * (t & 1), 0);     // the S buffer may be overwritten (by S(t+2))
       if (RELPOS) {
         const int sb = t % BD_STAGES;
         ATT_WAIT(bd_full + 8 * sb, (uint32_t)((t / BD_STAGES) & 1));
         const float* a = bd_lane + sb * (BD_STAGE_BYTES / 4);
 #pragma unroll
-        for (int j = 0; j < KB; ++j) s[j] += a[j];
+        for (int j = 0; j < 32; ++j) s[j] += a[j];
         __syncwarp();
         if (lane == 0) mbar_arrive_local(bd_empty + 8 * sb);
       }
-      if (J0 + KB > len) {
+      if (J0 + 32 > len) {
 #pragma unroll
-        for (int j = 0; j < KB; ++j) if (J0 + j >= len) s[j] = -INFINITY;
+        for (int j = 0; j < 32; ++j) if (J0 + j >= len) s[j] = -INFINITY;
       }
       float mt = s[0];
 #pragma unroll
-      for (int j = 1; j < KB; ++j) mt = fmaxf(mt, s[j]);
-      const float m_new = fmaxf(m_run, mt * scale);            // scale > 0: max commutes with the scaling
+      for (int j = 1; j < 32; ++j) mt = fmaxf(mt, s[j]);
+      // row maximum over both halves
+      float* xs = xch + (t & 1) * 256;
+      xs[g * 128 + rloc] = mt;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mt = fmaxf(mt, xs[(g ^ 1) * 128 + rloc]);
+      const float m_new = fmaxf(m_run, mt * scale);            // scale > 0: max commutes with the scaling; a fully masked half gives -inf
       const float alpha = __expf(m_run - m_new);               // first tile: exp(-inf) = 0
       float lsum = 0.f;
 #pragma unroll
-      for (int j = 0; j < KB; ++j) {
+      for (int j = 0; j < 32; ++j) {
         s[j] = __expf(fmaf(s[j], scale, -m_new));              // masked: exp(-inf) = 0
         lsum += s[j];
       }
@@ -287,56 +306,49 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
       if (t > 0) {   // O(t-1) is complete (and P(t-1) has been read): fold it in with the rescale of step t-1
         ATT_WAIT(o_full + 8 * ((t - 1) & 1), (uint32_t)(((t - 1) >> 1) & 1));
         tcgen05_fence_after();
+        float ot[32];
+        tmem_ld32_nowait(tmem_base + tlane + TM_O + (uint32_t)((t - 1) & 1) * 64 + cg, ot);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float ot[32];
-          tmem_ld32_nowait(tmem_base + tlane + TM_O + (uint32_t)((t - 1) & 1) * 64 + c * 32, ot);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o_acc[c * 32 + j] = fmaf(o_acc[c * 32 + j], alpha_prev, ot[j]);
-        }
+        for (int j = 0; j < 32; ++j) o_acc[j] = fmaf(o_acc[j], alpha_prev, ot[j]);
       }
       alpha_prev = alpha;
       {  // P(t) hi / lo -> TMEM
         float hv[32];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int j = 0; j < 32; ++j) hv[j] = espb::tf32_hi(s[j]);
+        tmem_st32(tmem_base + tlane + TM_PHI + cg, hv);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) hv[j] = espb::tf32_hi(s[c * 32 + j]);
-          tmem_st32(tmem_base + tlane + TM_PHI + c * 32, hv);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) hv[j] = espb::tf32_lo(s[c * 32 + j], hv[j]);
-          tmem_st32(tmem_base + tlane + TM_PLO + c * 32, hv);
-        }
+        for (int j = 0; j < 32; ++j) hv[j] = espb::tf32_lo(s[j], hv[j]);
+        tmem_st32(tmem_base + tlane + TM_PLO + cg, hv);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(p_full, 0);
       }
     }
-    {  // last tile's O, normalise, store hi/lo
+    {  // last tile's O, total row sum, normalise, store hi/lo
       const int t = nkt - 1;
+      float* xs = xch + ((t + 1) & 1) * 256;
+      xs[g * 128 + rloc] = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      const float inv = 1.f / (l_run + xs[(g ^ 1) * 128 + rloc]);
       ATT_WAIT(o_full + 8 * (t & 1), (uint32_t)((t >> 1) & 1));
       tcgen05_fence_after();
-      const float inv = 1.f / l_run;
-      float* o = p.out + ((long long)b * p.T + row) * p.ldo + h * DK;
+      float* o = p.out + ((long long)b * p.T + row) * p.ldo + h * DK + cg;
+      float ot[32];
+      tmem_ld32_nowait(tmem_base + tlane + TM_O + (uint32_t)(t & 1) * 64 + cg, ot);
+      tmem_ld_wait();
+      if (row < p.T) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float ot[32];
-        tmem_ld32_nowait(tmem_base + tlane + TM_O + (uint32_t)(t & 1) * 64 + c * 32, ot);
-        tmem_ld_wait();
-        if (row < p.T) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 hi, lo;
-            const float* oa = o_acc + c * 32 + j;
-            const float v0 = fmaf(oa[0], alpha_prev, ot[j]) * inv, v1 = fmaf(oa[1], alpha_prev, ot[j + 1]) * inv;
-            const float v2 = fmaf(oa[2], alpha_prev, ot[j + 2]) * inv, v3 = fmaf(oa[3], alpha_prev, ot[j + 3]) * inv;
-            hi.x = espb::tf32_hi(v0); hi.y = espb::tf32_hi(v1); hi.z = espb::tf32_hi(v2); hi.w = espb::tf32_hi(v3);
-            lo.x = espb::tf32_lo(v0, hi.x); lo.y = espb::tf32_lo(v1, hi.y); lo.z = espb::tf32_lo(v2, hi.z); lo.w = espb::tf32_lo(v3, hi.w);
-            *reinterpret_cast<float4*>(o + c * 32 + j) = hi;
-            *reinterpret_cast<float4*>(o + p.out_plane + c * 32 + j) = lo;
-          }
+        for (int j = 0; j < 32; j += 4) {
+          float4 hi, lo;
+          const float v0 = fmaf(o_acc[j], alpha_prev, ot[j]) * inv, v1 = fmaf(o_acc[j + 1], alpha_prev, ot[j + 1]) * inv;
+          const float v2 = fmaf(o_acc[j + 2], alpha_prev, ot[j + 2]) * inv, v3 = fmaf(o_acc[j + 3], alpha_prev, ot[j + 3]) * inv;
+          hi.x = espb::tf32_hi(v0); hi.y = espb::tf32_hi(v1); hi.z = espb::tf32_hi(v2); hi.w = espb::tf32_hi(v3);
+          lo.x = espb::tf32_lo(v0, hi.x); lo.y = espb::tf32_lo(v1, hi.y); lo.z = espb::tf32_lo(v2, hi.z); lo.w = espb::tf32_lo(v3, hi.w);
+          *reinterpret_cast<float4*>(o + j) = hi;
+          *reinterpret_cast<float4*>(o + p.out_plane + j) = lo;
         }
       }
     }
@@ -351,7 +363,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
 
 template <bool RELPOS>
 int launch_flash(const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmBD, const AttnParams& p, cudaStream_t stream) {
-  constexpr int smem = 2 * KV_STAGES * KV_STAGE_BYTES + (RELPOS ? BD_STAGES * BD_STAGE_BYTES : 0) + 1024 + 256;
+  constexpr int smem = 2 * KV_STAGES * KV_STAGE_BYTES + (RELPOS ? BD_STAGES * BD_STAGE_BYTES : 0) + 1024 + 256 + 2048;
   static_assert(smem <= 232448, "dynamic shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
