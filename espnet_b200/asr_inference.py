@@ -104,7 +104,7 @@ def build_model_from_file(config_file, model_file=None, device="cuda"):
 
 
 # keywords of the reference constructor that would change the result if honoured (refused unless left at their defaults) ...
-_REFUSED_KWARGS = {"lm_train_config", "lm_file", "ngram_file", "transducer_conf", "streaming", "quantize_asr_model", "quantize_lm",
+_REFUSED_KWARGS = {"ngram_file", "transducer_conf", "streaming", "quantize_asr_model", "quantize_lm",
                    "enh_s2t_task", "hugging_face_decoder", "multi_asr", "partial_ar", "lid_prompt",
                    "lang_prompt_token", "nlp_prompt_token", "prompt_token_file", "time_sync"}
 # ... and those that cannot (accepted without a warning)
@@ -117,7 +117,7 @@ class Speech2Text:
                  beam_size: int = 20, ctc_weight: float = 0.5, lm_weight: float = 1.0, ngram_weight: float = 0.9,
                  penalty: float = 0.0, nbest: int = 1, maxlenratio: float = 0.0, minlenratio: float = 0.0,
                  normalize_length: bool = False, batch_size: int = 1, token_type: Optional[str] = None, bpemodel: Optional[str] = None,
-                 asr_model: Optional[ESPnetASRModel] = None, asr_train_args=None, **unused):
+                 asr_model: Optional[ESPnetASRModel] = None, asr_train_args=None, lm_train_config=None, lm_file=None, lm=None, **unused):
         if dtype != "float32":
             raise NotImplementedError("espnet_b200 computes in float32 (the reference's inference dtype)")
         # Reference keywords (asr_inference.py:86-127) that select a different decoding algorithm must not be dropped silently.
@@ -140,6 +140,12 @@ class Speech2Text:
         token_list = asr_model.token_list
         decoder = asr_model.decoder if ctc_weight != 1.0 else None  # espnet_model.py:167-173
         scorers = dict(decoder=decoder, ctc=asr_model.ctc)
+        if lm is None and lm_train_config is not None:      # LM shallow fusion (asr_inference.py:178-191): scorers["lm"] = lm.lm
+            from .lm import build_lm_from_file
+
+            lm, self.lm_train_args = build_lm_from_file(lm_train_config, lm_file, device)
+        if lm is not None:
+            scorers["lm"] = lm.to(device).eval()
         weights = dict(decoder=1.0 - ctc_weight, ctc=ctc_weight, lm=lm_weight, ngram=ngram_weight, length_bonus=penalty)
         self.beam_search = BatchBeamSearch(scorers, weights, beam_size, len(token_list), asr_model.sos, asr_model.eos,
                                            token_list=token_list, pre_beam_score_key=None if ctc_weight == 1.0 else "full",

@@ -411,17 +411,62 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* _
     qs[w * QST + d] = (w < W) ? q[((long long)(u * Wall + w0 + w)) * D + h * DK + d] : 0.f;
   }
   const float rs = 8.0f;   // sqrt(d_k)
+  const int sa = min(g, W - 1), sb = min(g + 8, W - 1);
+  __syncthreads();         // qs is complete
+
+  // ================================================================= K phase: S[slot][t] = Q[slot][:] . K[t][:]
+  // A = Q (16 slot rows x 8 d per k-step, the same for every tile: split once into registers), B = K^T (8 d x 8 frames): warp w owns
+  // frames 8w..8w+7 of each 64-frame tile, so every K element is read from smem and split exactly once (the earlier layout -- A = K rows,
+  // B = Q^T -- split every K element in two warps and re-split Q for every tile: 3x the instructions of this loop; the kernel is
+  // issue-bound, not HBM-bound: ncu r01 30 % tensor pipe, 2.9 TB/s).
+  {
+    uint32_t qh[8][4], ql[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      split_tf32(qs[g * QST + ks * 8 + t4], qh[ks][0], ql[ks][0]);
+      split_tf32(qs[(g + 8) * QST + ks * 8 + t4], qh[ks][1], ql[ks][1]);
+      split_tf32(qs[g * QST + ks * 8 + t4 + 4], qh[ks][2], ql[ks][2]);
+      split_tf32(qs[(g + 8) * QST + ks * 8 + t4 + 4], qh[ks][3], ql[ks][3]);
+    }
+    for (int i = 0; i < nt; ++i) {
+      cp_async_wait<S - 2>();               // this thread's copies of tile i have landed ...
+      __syncthreads();                      // ... and everyone's; all warps are done with tile i-1, whose slot is refilled next
+      issue(i + S - 1);
+      const float* tile = ring + (i % S) * TILE_F;
+      const int tb = i * TR, rows = min(TR, T - tb);
+      const int f0 = warp * 8;
+      if (f0 < rows) {
+        // one accumulator per product term: three independent 8-deep mma chains instead of one 24-deep chain
+        float c[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* kr = tile + (f0 + g) * KST + t4;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          uint32_t bh[2], bl[2];
+          split_tf32(kr[ks * 8], bh[0], bl[0]);
+          split_tf32(kr[ks * 8 + 4], bh[1], bl[1]);
+          mma_m16n8k8_tf32(c1, ql[ks], bh);
+          mma_m16n8k8_tf32(c2, qh[ks], bl);
+          mma_m16n8k8_tf32(c, qh[ks], bh);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[e] += c1[e] + c2[e];   // small terms combined first
+        const int fa = tb + f0 + 2 * t4;                      // C fragment: rows (slots) g, g+8; columns (frames) 2*t4, 2*t4+1
+        if (g < W) { if (fa < T) sc[g * Tmax + fa] = c[0] / rs; if (fa + 1 < T) sc[g * Tmax + fa + 1] = c[1] / rs; }
+        if (g + 8 < W) { if (fa < T) sc[(g + 8) * Tmax + fa] = c[2] / rs; if (fa + 1 < T) sc[(g + 8) * Tmax + fa + 1] = c[3] / rs; }
+      }
+    }
+  }
+
+  // ================================================================= V phase: O[slot][d] = sum_t P[slot][t] V[t][d]
   float acc[8][4];
 #pragma unroll
   for (int n8 = 0; n8 < 8; ++n8) { acc[n8][0] = 0.f; acc[n8][1] = 0.f; acc[n8][2] = 0.f; acc[n8][3] = 0.f; }
-  const int sa = min(g, W - 1), sb = min(g + 8, W - 1);
-
-  for (int i = 0; i < NT; ++i) {
-    cp_async_wait<S - 2>();               // this thread's copies of tile i have landed ...
-    __syncthreads();                      // ... and everyone's; all warps are done with tile i-1, whose slot is refilled next
+  for (int i = nt; i < NT; ++i) {
+    cp_async_wait<S - 2>();
+    __syncthreads();
     issue(i + S - 1);
     if (i == nt) {
-      // ---- softmax over t per slot (no memory mask: batch_score passes none, transformer_decoder.py:294-303)
+      // ---- softmax over t per slot (no memory mask: batch_score passes none, transformer_decoder.py:294-303); the first V tiles land meanwhile
       for (int w = warp; w < W; w += 8) {
         float* r = sc + w * Tmax;
         float mx = -INFINITY;
@@ -435,35 +480,7 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* _
       __syncthreads();
     }
     const float* tile = ring + (i % S) * TILE_F;
-    if (i < nt) {
-      // ---- scores: A = K tile rows (16 per warp quarter), B = Q^T (n-tile of 8 slots per warp half), K-dim = d
-      const int tb = i * TR, rows = min(TR, T - tb);
-      const int r0 = (warp & 3) * 16, nb = warp >> 2;
-      if (r0 < rows && nb * 8 < W) {
-        // one accumulator per product term: three independent 8-deep mma chains instead of one 24-deep chain
-        float c[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const int k0 = ks * 8;
-          uint32_t ah[4], al[4], bh[2], bl[2];
-          split_tf32(tile[(r0 + g) * KST + k0 + t4], ah[0], al[0]);
-          split_tf32(tile[(r0 + g + 8) * KST + k0 + t4], ah[1], al[1]);
-          split_tf32(tile[(r0 + g) * KST + k0 + t4 + 4], ah[2], al[2]);
-          split_tf32(tile[(r0 + g + 8) * KST + k0 + t4 + 4], ah[3], al[3]);
-          split_tf32(qs[(nb * 8 + g) * QST + k0 + t4], bh[0], bl[0]);
-          split_tf32(qs[(nb * 8 + g) * QST + k0 + t4 + 4], bh[1], bl[1]);
-          mma_m16n8k8_tf32(c1, al, bh);
-          mma_m16n8k8_tf32(c2, ah, bl);
-          mma_m16n8k8_tf32(c, ah, bh);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) c[e] += c1[e] + c2[e];   // small terms combined first
-        const int s0 = nb * 8 + 2 * t4;
-        const int ta = tb + r0 + g, tbb = ta + 8;
-        if (s0 < W) { if (ta < T) sc[s0 * Tmax + ta] = c[0] / rs; if (tbb < T) sc[s0 * Tmax + tbb] = c[2] / rs; }
-        if (s0 + 1 < W) { if (ta < T) sc[(s0 + 1) * Tmax + ta] = c[1] / rs; if (tbb < T) sc[(s0 + 1) * Tmax + tbb] = c[3] / rs; }
-      }
-    } else {
+    {
       // ---- context: A = P (16 slot rows, clamped to W-1), B = V tile, K-dim = t (warp w takes the 8-frame k-step w of the tile)
       const int tb = (i - nt) * TR, rows = min(TR, T - tb);
       if (warp * 8 < rows) {
@@ -502,6 +519,152 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* _
 #pragma unroll
     for (int ww = 0; ww < 8; ++ww) a += red[((long long)ww * 16 + w) * DK + d];
     store_split(ctx + ((long long)(u * Wall + w0 + w)) * D + h * DK + d, ctx_plane, a);
+  }
+}
+
+// ---------------------------------------------------------------- cross-attention, single pass (d_k = 64, beam <= 16, any T)
+// Flash-decoding inside a block: K and V tiles of 64 frames stream TOGETHER through an S-deep cp.async ring (no [W][T] score buffer, so twice
+// the bytes are in flight per SM and T is unbounded); warp w owns frames 8w..8w+7 of every tile and keeps its own online-softmax state
+// (running max / partial sum per slot, partial context [16][64] in mma accumulators); the eight partial results are merged once at the end.
+//   scores  C[16 slots][8 frames] = Q (A, split once into registers / smem) x K^T (B): every K element is read and split once
+//   context O[16 slots][64]      += P (A = the C fragment re-used in place: the k index of the second product is simply a permutation of
+//                                   the warp's 8 frames, lane t4 holds frames 2 t4, 2 t4 + 1) x V (B rows picked with the same permutation)
+template <int S>
+__global__ void __launch_bounds__(256, 2) dec_src_attn_flash_kernel(const float* __restrict__ q, const float* __restrict__ kmem, const float* __restrict__ vmem,
+                                                                    int Tmax, const int* __restrict__ lens, int W, int D, int H,
+                                                                    float* __restrict__ ctx, long long ctx_plane, int w0, int Wall) {
+  constexpr int DK = 64, QST = 68, ST = 68, TR = 64, TILE_F = TR * ST, STAGE_F = 2 * TILE_F;
+  extern __shared__ float sm[];  // q lo [16][68] | ring [S][K [64][68] | V [64][68]] (reused for the cross-warp merge)
+  espb::pdl_trigger();
+  espb::pdl_wait();
+  const int u = blockIdx.x / H, h = blockIdx.x % H;
+  const int T = lens[u];
+  float* qlo = sm;
+  float* ring = qlo + 16 * QST;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const float4* kb = reinterpret_cast<const float4*>(kmem + ((long long)(u * H + h) * Tmax) * DK);
+  const float4* vb = reinterpret_cast<const float4*>(vmem + ((long long)(u * H + h) * Tmax) * DK);
+  const int nt = (T + TR - 1) / TR;
+  auto issue = [&](int i) {
+    if (i < nt) {
+      const int tb = i * TR;
+      float* dst = ring + (i % S) * STAGE_F;
+#pragma unroll
+      for (int j = threadIdx.x; j < 2 * TR * 16; j += 256) {
+        const int isv = j >> 10, rr = (j >> 4) & 63, cc = j & 15;
+        const bool ok = tb + rr < T;      // frames past the utterance are zero-filled (src-size 0)
+        cp_async16_zfill(dst + isv * TILE_F + rr * ST + cc * 4, (isv ? vb : kb) + (ok ? (long long)(tb + rr) * 16 + cc : 0), ok ? 16 : 0);
+      }
+    }
+    cp_async_commit();                    // one (possibly empty) group per tile index keeps the wait_group arithmetic uniform
+  };
+#pragma unroll
+  for (int i = 0; i < S - 1; ++i) issue(i);
+  // Q A-fragments: hi parts in registers, lo parts in shared memory (register budget: 128 per thread at two blocks per SM)
+  uint32_t qh[8][4];
+  {
+    const float* qg = q + ((long long)(u * Wall + w0)) * D + h * DK;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = g + (e & 1) * 8, col = ks * 8 + t4 + (e >> 1) * 4;
+        const float x = (row < W) ? __ldg(qg + (long long)row * D + col) : 0.f;
+        uint32_t lo;
+        split_tf32(x, qh[ks][e], lo);
+        if (warp == 0) qlo[row * QST + col] = __uint_as_float(lo);
+      }
+    }
+  }
+  const float inv_rs = 0.125f;   // 1 / sqrt(d_k), exact
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float acc[8][4];
+#pragma unroll
+  for (int n8 = 0; n8 < 8; ++n8) { acc[n8][0] = 0.f; acc[n8][1] = 0.f; acc[n8][2] = 0.f; acc[n8][3] = 0.f; }
+  const int f0 = warp * 8;
+
+  for (int i = 0; i < nt; ++i) {
+    cp_async_wait<S - 2>();               // this thread's copies of tile i have landed ...
+    __syncthreads();                      // ... and everyone's (also orders the qlo writes before the first use); tile i-1's slot is refilled next
+    issue(i + S - 1);
+    const int tb = i * TR;
+    if (tb + f0 >= T) continue;           // warp-uniform: none of this warp's frames exists
+    const float* kt = ring + (i % S) * STAGE_F;
+    const float* vt = kt + TILE_F;
+    float c[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* kr = kt + (f0 + g) * ST + t4;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      uint32_t bh[2], bl[2], al[4];
+      split_tf32(kr[ks * 8], bh[0], bl[0]);
+      split_tf32(kr[ks * 8 + 4], bh[1], bl[1]);
+      al[0] = __float_as_uint(qlo[g * QST + ks * 8 + t4]); al[1] = __float_as_uint(qlo[(g + 8) * QST + ks * 8 + t4]);
+      al[2] = __float_as_uint(qlo[g * QST + ks * 8 + t4 + 4]); al[3] = __float_as_uint(qlo[(g + 8) * QST + ks * 8 + t4 + 4]);
+      mma_m16n8k8_tf32(c1, al, bh);
+      mma_m16n8k8_tf32(c2, qh[ks], bl);
+      mma_m16n8k8_tf32(c, qh[ks], bh);
+    }
+    // scores of slots g (c[0], c[1]) and g+8 (c[2], c[3]) for frames fa, fa+1; no memory mask beyond the utterance's own frames
+    const int fa = tb + f0 + 2 * t4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[e] = (c[e] + (c1[e] + c2[e])) * inv_rs;
+    if (fa >= T) { c[0] = -INFINITY; c[2] = -INFINITY; }
+    if (fa + 1 >= T) { c[1] = -INFINITY; c[3] = -INFINITY; }
+    float x0 = fmaxf(c[0], c[1]), x1 = fmaxf(c[2], c[3]);
+    x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1));
+    x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+    const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);          // finite: frame tb + f0 exists
+    const float a0 = expf(m0 - n0), a1 = expf(m1 - n1);          // first tile: exp(-inf) = 0
+    const float p0 = expf(c[0] - n0), p1 = expf(c[1] - n0), p2 = expf(c[2] - n1), p3 = expf(c[3] - n1);
+    l0 = fmaf(l0, a0, p0 + p1); l1 = fmaf(l1, a1, p2 + p3);      // this lane's share of the row sums
+    m0 = n0; m1 = n1;
+    uint32_t ah[4], alo[4];
+    split_tf32(p0, ah[0], alo[0]); split_tf32(p2, ah[1], alo[1]);   // A fragment: (row g, k t4) = frame 2 t4; (row g+8, k t4)
+    split_tf32(p1, ah[2], alo[2]); split_tf32(p3, ah[3], alo[3]);   //             (row g, k t4+4) = frame 2 t4 + 1; (row g+8, k t4+4)
+    const float* vr = vt + (f0 + 2 * t4) * ST + g;
+#pragma unroll
+    for (int n8 = 0; n8 < 8; ++n8) {
+      acc[n8][0] *= a0; acc[n8][1] *= a0; acc[n8][2] *= a1; acc[n8][3] *= a1;
+      uint32_t bh[2], bl[2];
+      split_tf32(vr[n8 * 8], bh[0], bl[0]);            // B fragment: (k t4, n g) = V[frame 2 t4][8 n8 + g]
+      split_tf32(vr[ST + n8 * 8], bh[1], bl[1]);       //             (k t4+4, n g) = V[frame 2 t4 + 1][8 n8 + g]
+      mma3_tf32(acc[n8], ah, alo, bh, bl);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- merge of the eight warps: red[warp][slot 16][66] = (O[64], m, l) in the ring
+  float* red = ring;
+  static_assert(S * STAGE_F >= 8 * 16 * 66, "merge scratch must fit in the ring");
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+#pragma unroll
+  for (int n8 = 0; n8 < 8; ++n8) {
+    float* r0p = red + ((long long)warp * 16 + g) * 66 + n8 * 8 + 2 * t4;
+    float* r1p = red + ((long long)warp * 16 + g + 8) * 66 + n8 * 8 + 2 * t4;
+    r0p[0] = acc[n8][0]; r0p[1] = acc[n8][1];
+    r1p[0] = acc[n8][2]; r1p[1] = acc[n8][3];
+  }
+  if (t4 == 0) {
+    red[((long long)warp * 16 + g) * 66 + 64] = m0; red[((long long)warp * 16 + g) * 66 + 65] = l0;
+    red[((long long)warp * 16 + g + 8) * 66 + 64] = m1; red[((long long)warp * 16 + g + 8) * 66 + 65] = l1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < W * DK; i += blockDim.x) {
+    const int w = i / DK, d = i % DK;
+    float M = -INFINITY;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) M = fmaxf(M, red[((long long)ww * 16 + w) * 66 + 64]);
+    float L = 0.f, a = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) {
+      const float* r = red + ((long long)ww * 16 + w) * 66;
+      const float e = expf(r[64] - M);      // a warp without frames: exp(-inf) = 0
+      L = fmaf(r[65], e, L);
+      a = fmaf(r[d], e, a);
+    }
+    store_split(ctx + ((long long)(u * Wall + w0 + w)) * D + h * DK + d, ctx_plane, a / L);
   }
 }
 
@@ -787,6 +950,11 @@ __global__ void anc_update_kernel(const int* __restrict__ anc, int* __restrict__
   if (threadIdx.x == 0) n_anc[(long long)s * anc_ld + pos] = p;
 }
 
+__device__ __forceinline__ float logaddexp_fast(float a, float b) {
+  const float m = fmaxf(a, b);
+  return m + __logf(__expf(a - m) + __expf(b - m));
+}
+
 // New CTC forward variables of each surviving slot: the recursion of ctc_prefix_score.py:128-164 for (parent state, chosen token),
 // storing r[t][0..1].  One warp per slot: lanes prefetch 32 frames of (log_phi, x[t,c], x[t,blank]) in parallel, then the warp walks
 // the 32 sequential steps with shuffles (the dependent chain is two logaddexp per frame); lane l keeps frame l for a coalesced store.
@@ -828,8 +996,10 @@ __global__ void __launch_bounds__(128) ctc_advance_kernel(const float* __restric
     const int cnt = min(32, T - t0);
     for (int i = 0; i < cnt; ++i) {
       const float ph = __shfl_sync(0xffffffffu, phi, i), c1 = __shfl_sync(0xffffffffu, xc, i), b1 = __shfl_sync(0xffffffffu, xb, i);
-      const float nrn = logaddexp(rn, ph) + c1;
-      const float nrb = logaddexp(rn, rb) + b1;
+      // The two log-add-exp of a frame are the whole critical path of this kernel (T sequential frames): ex2 / lg2 approximations
+      // (2 ulp) instead of expf / logf cut the dependent chain from ~25 to ~8 instructions; the error stays ~1e-7 relative per frame.
+      const float nrn = logaddexp_fast(rn, ph) + c1;
+      const float nrb = logaddexp_fast(rn, rb) + b1;
       rn = nrn; rb = nrb;
       if (lane == i) { my_n = rn; my_b = rb; }
     }
@@ -857,6 +1027,53 @@ __global__ void __launch_bounds__(256) transpose_tv_kernel(const float* __restri
 }
 
 __global__ void step_inc_kernel(int* step) { *step += 1; }
+
+// ---------------------------------------------------------------- LM shallow fusion helpers (espnet2/lm/transformer_lm.py, beam_search.py:264-293)
+// Embedding rows of the newest tokens as a split [2][n][E] GEMM operand (TransformerLM.embed, then encoder.embed[0] = Linear).
+__global__ void gather_rows_split_kernel(const int* __restrict__ tok, const float* __restrict__ emb, int E, float* __restrict__ out, long long plane) {
+  espb::pdl_trigger();
+  espb::pdl_wait();
+  const int s = blockIdx.x;
+  const float* e = emb + (long long)tok[s] * E;
+  for (int c = threadIdx.x; c < E; c += blockDim.x) store_split(out + (long long)s * E + c, plane, e[c]);
+}
+// encoder.embed[3..4]: ReLU, then PositionalEncoding x * sqrt(D) + pe[pos] (embedding.py:85-95) or identity (pos_enc None), in place.
+__global__ void relu_posenc_kernel(float* __restrict__ x, int D, const float* __restrict__ pe, int pos, const int* __restrict__ step_ptr, float scale) {
+  espb::pdl_trigger();
+  espb::pdl_wait();
+  if (step_ptr) pos += *step_ptr;
+  const int s = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float v = fmaxf(x[(long long)s * D + c], 0.f);
+    if (pe) v = v * scale + pe[(long long)pos * D + c];
+    x[(long long)s * D + c] = v;
+  }
+}
+// weighted sum of two score matrices as the reference forms it: (wa * a) + (wb * b), each product rounded (no fma)
+__global__ void axpby_kernel(const float* __restrict__ a, float wa, const float* __restrict__ b, float wb, float* __restrict__ out, long long n) {
+  espb::pdl_trigger();
+  espb::pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fadd_rn(__fmul_rn(wa, a[i]), __fmul_rn(wb, b[i]));
+}
+// per-scorer running scores of the new hypotheses (merge_scores, beam_search.py:264-293): new[ns] = prev[parent[ns]] + logp[parent[ns]][tok[ns]],
+// also recorded per step so that ended hypotheses can be read back.  a / b: two full scorers (decoder, lm); b may be null.
+__global__ void track_scores_kernel(const int* __restrict__ parent, const int* __restrict__ tok, const int* __restrict__ bp_parent,
+                                    const float* __restrict__ logp_a, const float* __restrict__ logp_b, int V, const float* __restrict__ prev_a,
+                                    const float* __restrict__ prev_b, float* __restrict__ new_a, float* __restrict__ new_b, float* __restrict__ hist_a,
+                                    float* __restrict__ hist_b, int step, const int* __restrict__ step_ptr, int n) {
+  if (step_ptr) step += *step_ptr;
+  const int ns = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ns >= n) return;
+  float va = 0.f, vb = 0.f;
+  if (bp_parent[(long long)step * n + ns] >= 0) {
+    const int p = parent[ns], t = tok[ns];
+    if (logp_a) va = prev_a[p] + logp_a[(long long)p * V + t];
+    if (logp_b) vb = prev_b[p] + logp_b[(long long)p * V + t];
+  }
+  if (logp_a) { new_a[ns] = va; hist_a[(long long)step * n + ns] = va; }
+  if (logp_b) { new_b[ns] = vb; hist_b[(long long)step * n + ns] = vb; }
+}
 
 __global__ void count_active_kernel(const int* __restrict__ active, int n, int* __restrict__ out) {
   __shared__ float red[33];
@@ -903,7 +1120,23 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
   while (lpr * 4 < dk) lpr <<= 1;
   for (int w0 = 0; w0 < W; w0 += 16) {   // the kernels keep <= 16 beam slots per block; wider beams stream K/V once per group of 16
     const int Wg = (W - w0 < 16) ? W - w0 : 16;
-    if (dk == 64 && !getenv("ESPNET_B200_SRC_ATTN_FFMA")) {
+    if (dk == 64 && !getenv("ESPNET_B200_SRC_ATTN_FFMA") && !getenv("ESPNET_B200_SRC_ATTN_TWOPASS")) {
+      // single-pass kernel: 3 stages of (K, V) tiles = 112 KB -> two blocks per SM, 128 KB of loads in flight per SM
+      using FlashFn = void (*)(const float*, const float*, const float*, int, const int*, int, int, int, float*, long long, int, int);
+      const FlashFn fn = dec_src_attn_flash_kernel<3>;
+      const size_t smem = (16 * 68 + 3 * 2 * 64 * 68) * sizeof(float);
+      static bool attr = false;
+      if (!attr) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+          espb_set_error("dec_src_attn: cannot raise dynamic shared memory"); return ESPB_ERR_CUDA;
+        }
+        attr = true;
+      }
+      espb::launch_pdl(fn, dim3(U * H), dim3(256), smem, stream, q, kmem, vmem, Tmax, lens, Wg, D, H, ctx, ctx_plane, w0, W);
+      ESPB_CHECK_LAUNCH();
+      continue;
+    }
+    if (dk == 64 && !getenv("ESPNET_B200_SRC_ATTN_FFMA")) {   // two-pass variant (scores of the whole utterance in smem), kept for A/B
       const size_t scs4 = ((size_t)Wg * Tmax + 3) & ~(size_t)3;
       const size_t fixed = (16 * 68 + scs4) * sizeof(float), tile_b = 64 * 72 * sizeof(float);
       // deepest ring that still lets two blocks share an SM (227 KB), else the deepest that fits one block
@@ -1031,6 +1264,37 @@ int espb_ctc_advance_f32(const float* logp, int U, int Tmax, int V, const int* l
 int espb_transpose_tv_f32(const float* x, int U, int Tmax, int V, float* xt, cudaStream_t stream) {
   dim3 grid((V + 31) / 32, (Tmax + 31) / 32, U), block(32, 8);
   transpose_tv_kernel<<<grid, block, 0, stream>>>(x, Tmax, V, xt);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_gather_rows_split_f32(const int* tok, const float* emb, int n, int E, float* out, long long plane, cudaStream_t stream) {
+  if (n <= 0) return ESPB_OK;
+  espb::launch_pdl(gather_rows_split_kernel, dim3(n), dim3(128), 0, stream, tok, emb, E, out, plane);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_relu_posenc_f32(float* x, int n, int D, const float* pe, int pos, const int* step_ptr, float scale, cudaStream_t stream) {
+  if (n <= 0) return ESPB_OK;
+  espb::launch_pdl(relu_posenc_kernel, dim3(n), dim3(128), 0, stream, x, D, pe, pos, step_ptr, scale);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_axpby_f32(const float* a, float wa, const float* b, float wb, float* out, long long n, cudaStream_t stream) {
+  if (n <= 0) return ESPB_OK;
+  espb::launch_pdl(axpby_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, a, wa, b, wb, out, n);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_track_scores_f32(const int* parent, const int* tok, const int* bp_parent, const float* logp_a, const float* logp_b, int V, const float* prev_a,
+                          const float* prev_b, float* new_a, float* new_b, float* hist_a, float* hist_b, int step, const int* step_ptr, int n,
+                          cudaStream_t stream) {
+  if (n <= 0) return ESPB_OK;
+  track_scores_kernel<<<(n + 127) / 128, 128, 0, stream>>>(parent, tok, bp_parent, logp_a, logp_b, V, prev_a, prev_b, new_a, new_b, hist_a, hist_b, step,
+                                                          step_ptr, n);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

@@ -63,12 +63,16 @@ _SIGS = {
     "espb_beam_select": [P] * 18 + [I] + [P, P, P] + [I, I, I, I, I, P, P, P, I, F, F, F, I, P, P, P, P, P, I, I, P],
     "espb_anc_update_i32": [P, P, I, P, I, P, I, P],
     "espb_step_inc_i32": [P, P],
+    "espb_gather_rows_split_f32": [P, P, I, I, P, L, P],
+    "espb_relu_posenc_f32": [P, I, I, P, I, P, F, P],
+    "espb_axpby_f32": [P, F, P, F, P, L, P],
+    "espb_track_scores_f32": [P, P, P, P, P, I, P, P, P, P, P, P, I, P, I, P],
     "espb_ctc_advance_f32": [P, I, I, I, P, I, I, I, P, P, P, P, P, I, P, P, P, I, P],
     "espb_transpose_tv_f32": [P, I, I, I, P, P],
     "espb_count_active_i32": [P, I, P, P],
 }
 
-ABI_VERSION = 3   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
+ABI_VERSION = 4   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["espb_last_error", "espb_abi_version", "espb_device_sm", "espb_frontend_blocks"])
 
 

@@ -42,11 +42,16 @@ class BatchBeamSearch(torch.nn.Module):
         self.penalty = float(weights.get("length_bonus", 0.0))
         self.decoder = scorers.get("decoder") if self.w_dec != 0 else None
         self.ctc = scorers.get("ctc") if self.w_ctc != 0 else None
+        # LM shallow fusion (asr_inference.py:178-191): a second full scorer with weight lm_weight
+        self.w_lm = float(weights.get("lm", 0.0)) if scorers.get("lm") is not None else 0.0
+        self.lm = scorers.get("lm") if self.w_lm != 0 else None
+        if self.w_lm < 0:
+            raise NotImplementedError("negative scorer weights")
         if self.decoder is None and self.ctc is None:
-            raise ValueError("no scorer with non-zero weight")
+            raise ValueError("no decoder / ctc scorer with non-zero weight")
         if self.decoder is not None and self.w_dec < 0 or self.w_ctc < 0:
             raise NotImplementedError("negative scorer weights")
-        self.nn_dict = torch.nn.ModuleDict({k: v for k, v in (("decoder", self.decoder), ("ctc", self.ctc)) if v is not None})
+        self.nn_dict = torch.nn.ModuleDict({k: v for k, v in (("decoder", self.decoder), ("ctc", self.ctc), ("lm", self.lm)) if v is not None})
         self.sos, self.eos, self.n_vocab, self.beam_size = sos, eos, vocab_size, beam_size
         self.token_list = token_list
         self.pre_beam_size = int(pre_beam_ratio * beam_size)
@@ -56,7 +61,7 @@ class BatchBeamSearch(torch.nn.Module):
         if self.decoder is not None and self.ctc is not None and not self.do_pre_beam:
             raise NotImplementedError("joint decoding without pre-beam (vocab <= 1.5*beam) is not implemented")
         self.normalize_length = normalize_length
-        self.full_scorers = {k: v for k, v in (("decoder", self.decoder),) if v is not None}
+        self.full_scorers = {k: v for k, v in (("decoder", self.decoder), ("lm", self.lm)) if v is not None}
         self.part_scorers = {k: v for k, v in (("ctc", self.ctc),) if v is not None}
         if beam_size > 32:
             raise NotImplementedError("beam_size > 32 (the per-utterance beam selection runs in one warp)")
@@ -64,7 +69,7 @@ class BatchBeamSearch(torch.nn.Module):
     # ---------------------------------------------------------------- search state (cached per shape so that CUDA graphs can be reused)
     def _state(self, dev, U, Tmax, W, V, cap, mode, P, g=0, end_detect=0):
         # end_detect is baked into the captured CUDA graphs (by-value kernel argument of beam_select): it is part of the key
-        key = (str(dev), U, Tmax, W, V, cap, mode, P, g, end_detect)
+        key = (str(dev), U, Tmax, W, V, cap, mode, P, g, end_detect, self.lm is not None)
         cache = getattr(self, "_state_cache", None)
         if cache is None:
             cache = self._state_cache = {}
@@ -94,6 +99,10 @@ class BatchBeamSearch(torch.nn.Module):
                 st["logp_ctc_t"] = f32(U * V, Tmax)
             else:
                 st["part"] = f32(n, V)
+        if self.lm is not None:   # second full scorer: combined full scores, per-scorer running scores (ping-pong) and their per-step record
+            st["full"] = f32(n, V)
+            st["sc_a"], st["sc_b"] = [f32(n), f32(n)], [f32(n), f32(n)]
+            st["hist_a"], st["hist_b"] = f32(cap, n), f32(cap, n)
         cache[key] = st
         return st
 
@@ -202,7 +211,7 @@ class BatchBeamSearch(torch.nn.Module):
             self._streams[key] = torch.cuda.Stream(device=dev)
         return self._streams[key]
 
-    def _collect(self, U, W, steps, maxlen, bp_parent, bp_token, e_count, e_step, e_slot, e_score, e_dec, e_ctc):
+    def _collect(self, U, W, steps, maxlen, bp_parent, bp_token, e_count, e_step, e_slot, e_score, e_dec, e_ctc, hist=None):
         """Host post-processing: rebuild token sequences from back-pointers and sort (beam_search.py:452-459).
         The back-pointer walk is vectorised over all ended hypotheses (one numpy gather per position)."""
         import numpy as np
@@ -232,10 +241,15 @@ class BatchBeamSearch(torch.nn.Module):
         length = step_h + 2 + at_max                                      # sos + (step+1) tokens (+ appended eos)
         seq_t = torch.from_numpy(seq)
         score_h, dec_h, ctc_h = sc[uu, ee], sd[uu, ee], sct[uu, ee]
+        lm_h = None
+        if hist is not None:   # LM fusion: the per-scorer scores were recorded per step (the beam kernel tracked their weighted sum)
+            ha, hb = hist[0][:steps].cpu().numpy(), hist[1][:steps].cpu().numpy()
+            dec_h, lm_h = (ha[step_h, slot_h], hb[step_h, slot_h]) if nh else (dec_h, np.zeros(0, np.float32))
         key = score_h / (length - 1) if self.normalize_length else score_h
         results = [[] for _ in range(U)]
         start = np.concatenate([[0], np.cumsum(cnt)])
         has_dec, has_ctc, has_pen = self.decoder is not None, self.ctc is not None, self.penalty != 0
+        has_lm = lm_h is not None
         for u in range(U):
             lo, hi = int(start[u]), int(start[u + 1])
             if hi == lo:
@@ -248,6 +262,8 @@ class BatchBeamSearch(torch.nn.Module):
                     scores["decoder"] = float(dec_h[i])
                 if has_ctc:
                     scores["ctc"] = float(ctc_h[i])
+                if has_lm:
+                    scores["lm"] = float(lm_h[i])
                 if has_pen:
                     scores["length_bonus"] = float(step_h[i] + 1)
                 hyps.append(Hypothesis(yseq=seq_t[i, : int(length[i])], score=float(score_h[i]), scores=scores))
@@ -303,6 +319,12 @@ class _SearchRun:
         if use_dec:
             bs.decoder.ws_tag = g
             self.dst = bs.decoder.init_memory(enc_split, U, Tmax, self.lens32, n, cap)
+        self.lst = None
+        if bs.lm is not None:
+            bs.lm.ws_tag = g
+            self.lst = bs.lm.init_cache(n, cap)
+            for k in ("sc_a", "sc_b"):
+                st[k][0].zero_(); st[k][1].zero_()
         self.logp_ctc = self.logp_tok = None
         self.tok_major = 0
         if use_ctc:
@@ -315,7 +337,8 @@ class _SearchRun:
                 call("espb_transpose_tv_f32", ptr(self.logp_ctc), U, Tmax, V, ptr(self.logp_tok))
                 _count()
         self.side = bs._side_stream(dev, g) if (use_ctc and use_dec) else None
-        self.buf_ver = (getattr(bs.decoder, "buf_version", 0), id(bs.decoder._packed)) if use_dec else None
+        self.buf_ver = ((getattr(bs.decoder, "buf_version", 0), id(bs.decoder._packed)) if use_dec else None,
+                        (getattr(bs.lm, "buf_version", 0), id(bs.lm._packed)) if bs.lm is not None else None)
 
     def step_body(self, i, cur, sp):
         """One search step. `sp` is None (host step index i) or the device step counter (graph mode: i is ignored)."""
@@ -349,28 +372,45 @@ class _SearchRun:
         if self.use_dec:
             bs.decoder.ws_tag = self.g
             logp_dec = bs.decoder.step(self.dst, iv, last_tok[cur], anc[cur], W, sp)
+        logp_lm, w_full, logp_full = None, bs.w_dec, logp_dec
+        if bs.lm is not None:
+            bs.lm.ws_tag = self.g
+            logp_lm = bs.lm.step(self.lst, iv, last_tok[cur], anc[cur], sp)
+            if self.use_dec:   # weighted sum of the full scorers, decoder first (batch_beam_search.py:293-300); the beam kernels then see one scorer of weight 1
+                call("espb_axpby_f32", ptr(logp_dec), bs.w_dec, ptr(logp_lm), bs.w_lm, ptr(st["full"]), n * V)
+                _count()
+                w_full, logp_full = 1.0, st["full"]
         if forked:
             main.wait_stream(side)
         if mode == 1:
-            ops.rows_topk(logp_dec, bs.w_dec, P, st["cand_ids"], st["cand_val"])
+            ops.rows_topk(logp_full, w_full, P, st["cand_ids"], st["cand_val"])
             call("espb_ctc_score_cands_f32", ptr(self.logp_tok), U, Tmax, V, ptr(lens32), 0, bs.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
                  ptr(last_tok[cur]), iv, ptr(sp), ptr(st["cand_ids"]), P, ptr(st["part"]), ptr(st["psi"]), ptr(st["valid"]), self.tok_major)
             _count()
         elif mode == 0:
-            ops.rows_topk(logp_dec, bs.w_dec, P, st["cand_ids"], st["cand_val"])
+            ops.rows_topk(logp_full, w_full, P, st["cand_ids"], st["cand_val"])
         else:
             call("espb_ctc_score_dense_f32", ptr(self.logp_ctc), U, Tmax, V, ptr(lens32), 0, bs.eos, W, ptr(r[cur]), ptr(s_prev[cur]),
                  ptr(last_tok[cur]), i, ptr(st["part"]))
             _count()
-            ops.rows_topk(st["part"], bs.w_ctc, P, st["cand_ids"], st["cand_val"])
+            if logp_lm is not None:   # CTC-only + LM: the LM is the only full scorer, no pre-beam: (w_lm * lm) + (w_ctc * ctc) over the vocabulary
+                call("espb_axpby_f32", ptr(logp_lm), bs.w_lm, ptr(st["part"]), bs.w_ctc, ptr(st["full"]), n * V)
+                _count()
+                ops.rows_topk(st["full"], 1.0, P, st["cand_ids"], st["cand_val"])
+            else:
+                ops.rows_topk(st["part"], bs.w_ctc, P, st["cand_ids"], st["cand_val"])
         call("espb_beam_select", ptr(score[cur]), ptr(sc_dec[cur]), ptr(sc_ctc[cur]), ptr(active[cur]), ptr(score[nxt]),
              ptr(sc_dec[nxt]), ptr(sc_ctc[nxt]), ptr(active[nxt]), ptr(last_tok[nxt]), ptr(parent), ptr(st["bp_parent"]),
              ptr(st["bp_token"]), ptr(st["e_count"]), ptr(st["e_step"]), ptr(st["e_slot"]), ptr(st["e_score"]), ptr(st["e_dec"]),
              ptr(st["e_ctc"]), st["ended_cap"], ptr(st["best_at"]), ptr(st["best_all"]), ptr(st["done"]), U, W, P, V, iv, ptr(sp),
-             ptr(st["maxlen"]), ptr(st["minlen"]), bs.eos, bs.w_dec, bs.w_ctc, bs.penalty, mode, ptr(st["cand_ids"]),
-             ptr(st["cand_val"]), ptr(logp_dec), ptr(st.get("part")), ptr(st.get("valid")), self.end_detect, cap)
+             ptr(st["maxlen"]), ptr(st["minlen"]), bs.eos, w_full, bs.w_ctc, bs.penalty, mode, ptr(st["cand_ids"]),
+             ptr(st["cand_val"]), ptr(logp_full), ptr(st.get("part")), ptr(st.get("valid")), self.end_detect, cap)
         _count()
-        if self.use_dec:
+        if logp_lm is not None:   # per-scorer scores of the chosen hypotheses (the beam kernel only tracked the combined full score)
+            call("espb_track_scores_f32", ptr(parent), ptr(last_tok[nxt]), ptr(st["bp_parent"]), ptr(logp_dec), ptr(logp_lm), V, ptr(st["sc_a"][cur]),
+                 ptr(st["sc_b"][cur]), ptr(st["sc_a"][nxt]), ptr(st["sc_b"][nxt]), ptr(st["hist_a"]), ptr(st["hist_b"]), iv, ptr(sp), n)
+            _count()
+        if self.use_dec or logp_lm is not None:
             call("espb_anc_update_i32", ptr(anc[cur]), ptr(anc[nxt]), cap + 1, ptr(parent), iv, ptr(sp), n)
             _count()
         if sp is not None:
@@ -438,5 +478,6 @@ class _SearchRun:
                     raise IndexError(f"CTC prefix scoring cannot extend hypotheses beyond the encoder output length + 1: utterance(s) {bad} of this group "
                                      f"still had live hypotheses at step {int(self.lens_cpu[u]) + 1} ({int(self.lens_cpu[u])} encoder frames, maxlen "
                                      f"{int(self.maxlen[u])}); lower maxlenratio or decode with ctc_weight=0")
+        hist = (st["hist_a"], st["hist_b"]) if self.bs.lm is not None else None
         return self.bs._collect(self.U, self.W, self.steps_run, self.maxlen, st["bp_parent"], st["bp_token"], st["e_count"], st["e_step"],
-                                st["e_slot"], st["e_score"], st["e_dec"], st["e_ctc"])
+                                st["e_slot"], st["e_score"], st["e_dec"], st["e_ctc"], hist)

@@ -151,6 +151,17 @@ int espb_beam_select(const float* score, const float* sc_dec, const float* sc_ct
                      const float* cand_val, const float* logp_dec, const float* part, const int* valid, int end_detect, int maxlen_cap,
                      cudaStream_t stream);
 int espb_anc_update_i32(const int* anc, int* n_anc, int anc_ld, const int* parent, int pos, const int* step_ptr, int n, cudaStream_t stream);
+/* ---- LM shallow fusion (espnet2/lm/transformer_lm.py:95-133 as a full scorer; wiring espnet2/bin/asr_inference.py:178-191) ---- */
+/* embedding rows of the newest tokens as a split [2][n][E] operand */
+int espb_gather_rows_split_f32(const int* tok, const float* emb, int n, int E, float* out, long long plane, cudaStream_t stream);
+/* x = relu(x); if pe: x = x * scale + pe[pos (+ *step_ptr)]   (legacy transformer/encoder.py:132-139, embedding.py:85-95) */
+int espb_relu_posenc_f32(float* x, int n, int D, const float* pe, int pos, const int* step_ptr, float scale, cudaStream_t stream);
+/* out = (wa * a) + (wb * b), products rounded separately: the weighted sum of scorer outputs (batch_beam_search.py:293-300) */
+int espb_axpby_f32(const float* a, float wa, const float* b, float wb, float* out, long long n, cudaStream_t stream);
+/* per-scorer running scores of the hypotheses chosen by espb_beam_select (merge_scores, beam_search.py:264-293), recorded per step */
+int espb_track_scores_f32(const int* parent, const int* tok, const int* bp_parent, const float* logp_a, const float* logp_b, int V, const float* prev_a,
+                          const float* prev_b, float* new_a, float* new_b, float* hist_a, float* hist_b, int step, const int* step_ptr, int n,
+                          cudaStream_t stream);
 int espb_step_inc_i32(int* step, cudaStream_t stream);
 int espb_count_active_i32(const int* active, int n, int* out, cudaStream_t stream);
 

@@ -476,16 +476,52 @@ _TABLE.update({"espb_log_softmax_rows_f32": _log_softmax_rows, "espb_argmax_rows
                "espb_count_active_i32": _count_active})
 
 
+def _gather_rows_split(tok, emb, n, E, out, plane):
+    _store(_flat(out), torch.arange(n * E).view(n, E), emb.view(-1, E)[tok.view(-1)[:n].long()], True, plane)
+
+
+def _relu_posenc(x, n, D, pe, pos, step_ptr, scale):
+    pos += _step(step_ptr)
+    xv = _flat(x)[: n * D].view(n, D)
+    v = torch.relu(xv)
+    if pe is not None:
+        v = v * torch.tensor(scale, dtype=torch.float32) + pe.view(-1, D)[pos]
+    xv.copy_(v)
+
+
+def _axpby(a, wa, b, wb, out, n):
+    f = lambda w: torch.tensor(w, dtype=torch.float32)  # noqa: E731
+    _flat(out)[:n] = f(wa) * _flat(a)[:n] + f(wb) * _flat(b)[:n]
+
+
+def _track_scores(parent, tok, bp_parent, logp_a, logp_b, V, prev_a, prev_b, new_a, new_b, hist_a, hist_b, step, step_ptr, n):
+    step += _step(step_ptr)
+    for ns in range(n):
+        ok = int(bp_parent.view(-1)[step * n + ns]) >= 0
+        p, t = int(parent.view(-1)[ns]), int(tok.view(-1)[ns])
+        for lp, prev, new, hist in ((logp_a, prev_a, new_a, hist_a), (logp_b, prev_b, new_b, hist_b)):
+            if lp is None:
+                continue
+            v = (prev.view(-1)[p] + lp.view(-1)[p * V + t]) if ok else torch.tensor(0.0)
+            new.view(-1)[ns] = v
+            hist.view(-1)[step * n + ns] = v
+
+
+_TABLE.update({"espb_gather_rows_split_f32": _gather_rows_split, "espb_relu_posenc_f32": _relu_posenc, "espb_axpby_f32": _axpby,
+               "espb_track_scores_f32": _track_scores})
+
+
 def install_search(monkeypatch):
     """install() + the CTC head, decoder and search modules; CUDA streams / graphs are taken out of the picture (host logic only)."""
     import contextlib
 
     import espnet_b200.ctc as ctc
     import espnet_b200.decoder as dec
+    import espnet_b200.lm as lmmod
     import espnet_b200.search as search
 
     install(monkeypatch)
-    for mod in (ctc, dec, search):
+    for mod in (ctc, dec, search, lmmod):
         monkeypatch.setattr(mod, "call", call, raising=True)
         monkeypatch.setattr(mod, "ptr", ptr, raising=True)
     class NoStream:   # stands in for torch.cuda.Stream: ordering is trivially sequential on the host

@@ -89,13 +89,13 @@ def test_end_of_search_log_lines(caplog):
 
 
 def test_speech2text_refuses_unimplemented_reference_keywords():
-    """lm_file / ngram_file / transducer_conf / streaming ... change the decoding algorithm: they must raise, not be swallowed (and they are
+    """ngram_file / transducer_conf / streaming ... change the decoding algorithm: they must raise, not be swallowed (and they are
     checked before any device work, so this runs without a GPU)."""
     import pytest
 
     import espnet_b200
 
-    for kw in (dict(lm_file="lm.pth"), dict(ngram_file="4gram.bin"), dict(transducer_conf={"search_type": "default"}), dict(streaming=True),
+    for kw in (dict(ngram_file="4gram.bin"), dict(transducer_conf={"search_type": "default"}), dict(streaming=True),
                dict(quantize_asr_model=True)):
         with pytest.raises(NotImplementedError, match=list(kw)[0]):
             espnet_b200.Speech2Text(asr_model=object(), **kw)
