@@ -205,6 +205,60 @@ class Speech2Text:
         return [self._results(h) for h in hyps]
 
     @torch.no_grad()
+    def batch_decode_sharded(self, speech: torch.Tensor, lengths: torch.Tensor, max_tokens: int = 256):
+        """Utterance-sharded decoding over the ranks of an initialised torch.distributed job (one process per GPU; the reference shards by
+        splitting the key file over processes, asr.sh:1591-1618): this rank decodes ITS utterances (speech (B_local, Lmax), pinned host or device)
+        and every rank receives the n-best token ids and scores of all utterances -- one all-gather of fixed-width records, no other
+        collective.  Returns (local results as batch_decode_padded, [rank][utterance][(token ids, score)])."""
+        import torch.distributed as dist
+
+        from . import sharding
+
+        import os
+        import time
+
+        t0 = time.perf_counter()
+        local = self.batch_decode_padded(speech, lengths)
+        t1 = time.perf_counter()
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        out = local, sharding.all_gather_results(local, self.nbest, max_tokens, world, device=self.device)
+        if os.environ.get("ESPB_BENCH_DEBUG"):
+            logger.warning(f"batch_decode_sharded: decode {1e3 * (t1 - t0):.1f} ms, exchange {1e3 * (time.perf_counter() - t1):.1f} ms")
+        return out
+
+    def decode_stream(self, batches, sharded: bool = False):
+        """Iterate over (speech (B, Lmax) pinned host memory, lengths) batches with the host-to-device copy of batch k+1 running on a copy
+        stream under the computation of batch k (double buffering; the device buffer of a batch is released to the copy stream once its
+        encoder pass has consumed it).  Yields what batch_decode_padded / batch_decode_sharded returns."""
+        if getattr(self, "_copy_stream", None) is None:    # one copy stream per instance: the caching allocator pools blocks per stream
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        copy_stream = self._copy_stream
+        main = torch.cuda.current_stream(self.device)
+
+        def start(item):
+            sp, ln = item
+            with torch.cuda.stream(copy_stream):
+                dev = sp.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return dev, ln, ev
+
+        it = iter(batches)
+        try:
+            nxt = start(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            dev, ln, ev = nxt
+            main.wait_event(ev)
+            dev.record_stream(main)
+            try:
+                nxt = start(next(it))
+            except StopIteration:
+                nxt = None
+            yield self.batch_decode_sharded(dev, ln) if sharded else self.batch_decode_padded(dev, ln)
+
+    @torch.no_grad()
     def __call__(self, speech: Union[torch.Tensor, np.ndarray]):
         logger.info("speech length: " + str(int(speech.shape[0])))
         return self.batch_decode([speech])[0]

@@ -86,7 +86,8 @@ def gemm(M, N, K, A, a_plane, lda, B, b_plane, ldb, C, ldc, *, c_plane=0, split_
     call("espb_gemm_f32", d, use_tc)
     if prof is not None:
         e1.record()
-        prof.append((2.0 * M * N * K * nbx * nby, e0, e1, use_tc == 2 and M * nbx * nby > 1024))   # last: CTA-pair kernel?
+        n_alg = band_t if band_t > 0 else N     # rel-pos band product: every row needs band_t of the N columns
+        prof.append((2.0 * M * n_alg * K * nbx * nby, e0, e1, use_tc == 2 and M * nbx * nby > 1024))   # last: CTA-pair kernel?
     _count()
     return bool(use_tc)
 

@@ -22,32 +22,36 @@ def shard_indices(n_utts: int, rank: int, world: int) -> List[int]:
 
 def pack_hypotheses(nbest_lists: Sequence[Sequence[Tuple[List[int], float]]], nbest: int, max_tokens: int, rows: int = None,
                     device="cpu") -> torch.Tensor:
+    import numpy as np
+
     rows = len(nbest_lists) if rows is None else rows
-    rec = torch.full((rows, nbest, 2 + max_tokens), -1, dtype=torch.int32)
+    rec = np.full((rows, nbest, 2 + max_tokens), -1, dtype=np.int32)
     rec[len(nbest_lists):, 0, 0] = PAD_ROW
     for i, hyps in enumerate(nbest_lists):
         for j, (toks, score) in enumerate(list(hyps)[:nbest]):
             toks = list(toks)[:max_tokens]
             rec[i, j, 0] = len(toks)
-            rec[i, j, 1] = torch.tensor(score, dtype=torch.float32).view(torch.int32)
+            rec[i, j, 1] = np.float32(score).view(np.int32)
             if toks:
-                rec[i, j, 2:2 + len(toks)] = torch.tensor(toks, dtype=torch.int32)
-    return rec.to(device)
+                rec[i, j, 2:2 + len(toks)] = toks
+    return torch.from_numpy(rec).to(device)
 
 
 def unpack_hypotheses(rec: torch.Tensor, nbest: int):
-    rec = rec.cpu()
+    import numpy as np
+
+    r = rec.cpu().numpy()
     out = []
-    for i in range(rec.shape[0]):
+    for i in range(r.shape[0]):
+        if int(r[i, 0, 0]) == PAD_ROW:
+            continue
         hyps = []
         for j in range(nbest):
-            n = int(rec[i, j, 0])
+            n = int(r[i, j, 0])
             if n < 0:
                 continue
-            score = float(rec[i, j, 1].view(torch.float32))
-            hyps.append((rec[i, j, 2:2 + n].tolist(), score))
-        if int(rec[i, 0, 0]) != PAD_ROW:
-            out.append(hyps)
+            hyps.append((r[i, j, 2:2 + n].tolist(), float(r[i, j, 1:2].view(np.float32)[0])))
+        out.append(hyps)
     return out
 
 
@@ -66,3 +70,18 @@ def gather_hypotheses(rec: torch.Tensor, world: int) -> torch.Tensor:
     out = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
     dist.all_gather_into_tensor(out.view(world * rows, *rec.shape[1:]), rec.contiguous())
     return out
+
+
+def results_to_records(results, nbest: int, max_tokens: int, device="cpu") -> torch.Tensor:
+    """Speech2Text result lists [(text, tokens, token_int, Hypothesis), ...] per utterance -> hypothesis records (token ids with sos / eos
+    stripped, as the result tuples carry them, and the total score)."""
+    return pack_hypotheses([[(r[2], float(r[3].score)) for r in res[:nbest]] for res in results], nbest, max_tokens, device=device)
+
+
+def all_gather_results(results, nbest: int, max_tokens: int, world: int, device="cpu"):
+    """The single exchange of the utterance-sharded path: every rank contributes the records of its own utterances and gets
+    [rank][utterance][(token ids, score), ...] of the whole job (NCCL on GPUs, gloo in the CPU tests)."""
+    rec = results_to_records(results, nbest, max_tokens, device=device)
+    allrec = gather_hypotheses(rec, world)
+    allrec = allrec.cpu()
+    return [unpack_hypotheses(allrec[r], nbest) for r in range(world)]

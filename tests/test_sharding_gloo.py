@@ -30,6 +30,42 @@ def _worker(rank, world, port, n_utts, q):
     dist.destroy_process_group()
 
 
+def _worker_results(rank, world, port, q):
+    """all_gather_results over Speech2Text-shaped result lists (with scores); rank 1 holds one utterance fewer and one empty n-best."""
+    from collections import namedtuple
+
+    from espnet_b200.sharding import all_gather_results
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    H = namedtuple("H", "score")
+    if rank == 0:
+        local = [[("a", ["x"], [3, 4, 5], H(-1.25)), ("b", ["y"], [3, 4], H(-2.5))], [("c", ["z"], [9], H(-0.125))]]
+    else:
+        local = [[]]
+    out = all_gather_results(local, nbest=2, max_tokens=6, world=world)
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_all_gather_results_two_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_results, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):      # every rank sees the whole job
+        out = got[r]
+        assert out[0] == [[([3, 4, 5], -1.25), ([3, 4], -2.5)], [([9], -0.125)]]
+        assert out[1] == [[]]
+
+
 def test_shard_and_gather_two_ranks():
     world, n_utts = 2, 7
     ctx = mp.get_context("spawn")
