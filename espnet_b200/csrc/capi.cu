@@ -28,7 +28,7 @@ bool pdl_enabled() {
 extern "C" {
 
 const char* espb_last_error(void) { return g_err; }
-int espb_abi_version(void) { return 4; }   // 3: espb_flash_attn_f32; 4: LM fusion helpers (gather_rows_split, relu_posenc, axpby, track_scores)
+int espb_abi_version(void) { return 5; }   // 3: espb_flash_attn_f32; 4: LM fusion helpers; 5: hop / window generality of the frontend entry points
 
 int espb_device_sm(int* major, int* minor) {
   int dev = 0;

@@ -46,8 +46,8 @@ class LogMel(torch.nn.Module):
         self.register_buffer("melmat", slaney_mel_matrix(fs, n_fft, n_mels, fmin, fmax))
 
 
-# feats tensors produced by the fused kernel -> per-block column sums (lets UtteranceMVN skip its reduction pass)
-_PARTIAL_SUMS = {}
+# The fused kernel also emits per-block column sums; they travel with the feats tensor object itself (attribute ``_espb_partial``), so that
+# UtteranceMVN can skip its reduction pass when it is handed exactly that tensor (no module-global state: re-entrant).
 
 
 class DefaultFrontend(torch.nn.Module):
@@ -62,11 +62,13 @@ class DefaultFrontend(torch.nn.Module):
         if isinstance(fs, str):
             s = fs.strip().lower()
             fs = int(float(s[:-1]) * {"k": 1000, "m": 1000000}[s[-1]]) if s[-1] in "km" else int(s)
-        if (n_fft, hop_length, win_length or n_fft, window, center, normalized, onesided, apply_stft) != (
-                512, 128, 512, "hann", True, False, True, True):
-            raise NotImplementedError("espnet_b200 DefaultFrontend implements the reference defaults only: n_fft=512, "
-                                      "hop_length=128, hann window, center=True, onesided, not normalized")
-        self.hop_length, self.n_fft, self.n_mels = hop_length, n_fft, n_mels
+        win_length = n_fft if win_length is None else int(win_length)
+        if (n_fft, center, normalized, onesided, apply_stft) != (512, True, False, True, True) or not (0 < win_length <= n_fft) or hop_length < 1:
+            raise NotImplementedError("espnet_b200 DefaultFrontend: n_fft=512, center=True, onesided, not normalized (any hop_length, "
+                                      "win_length <= 512, any torch window function or None)")
+        if window is not None and not hasattr(torch, f"{window}_window"):
+            raise ValueError(f"{window} window is not implemented")       # stft.py:41-42
+        self.hop_length, self.n_fft, self.n_mels, self.win_length, self.window = int(hop_length), n_fft, n_mels, win_length, window
         self.logmel = LogMel(fs=fs, n_fft=n_fft, n_mels=n_mels, fmin=fmin, fmax=fmax, htk=htk)
         self.frontend_type = "default"
         self._dev = None  # cached device-side constants
@@ -87,16 +89,25 @@ class DefaultFrontend(torch.nn.Module):
             starts.append(lo); counts.append(hi - lo); offsets.append(len(weights)); weights.extend(m[lo:hi, j].tolist())
         k = np.arange(256, dtype=np.float64)
         tw = np.stack([np.cos(2 * np.pi * k / 512), -np.sin(2 * np.pi * k / 512)], axis=1).astype(np.float32)
+        nk = np.outer(np.arange(16), np.arange(16)).astype(np.float64)          # [k1][n2] -> W256^{n2 k1} (four-step FFT twiddles)
+        twt = np.stack([np.cos(2 * np.pi * nk / 256), -np.sin(2 * np.pi * nk / 256)], axis=-1).reshape(256, 2).astype(np.float32)
+        # torch.stft: the window (win_length taps, periodic) is zero-padded on both sides to n_fft (stft.py:84-93)
+        if self.window is not None:
+            wwin = getattr(torch, f"{self.window}_window")(self.win_length, dtype=torch.float32)
+        else:
+            wwin = torch.ones(self.win_length, dtype=torch.float32)
+        left = (self.n_fft - self.win_length) // 2
+        wfull = torch.zeros(self.n_fft, dtype=torch.float32)
+        wfull[left:left + self.win_length] = wwin
         i32 = lambda a: torch.tensor(a, dtype=torch.int32, device=device)  # noqa: E731
-        self._dev = dict(key=key, start=i32(starts), count=i32(counts), offset=i32(offsets),
+        self._dev = dict(key=key, start=i32(starts), count=i32(counts), offset=i32(offsets), nnz=len(weights),
                          weight=torch.tensor(weights if weights else [0.0], dtype=torch.float32, device=device),
-                         tw=torch.from_numpy(tw).to(device),
-                         window=torch.hann_window(512, periodic=True, dtype=torch.float32).to(device))
+                         tw=torch.from_numpy(tw).to(device), twt=torch.from_numpy(twt).to(device), window=wfull.to(device))
         return self._dev
 
     @torch.no_grad()
     def forward(self, input: torch.Tensor, input_lengths: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """input (B, L) float32 CUDA, input_lengths (B,) int64 -> feats (B, 1 + Lmax//128, n_mels), feats_lens."""
+        """input (B, L) float32 CUDA, input_lengths (B,) int64 -> feats (B, 1 + Lmax//hop_length, n_mels), feats_lens."""
         if input.dim() != 2:
             raise NotImplementedError("espnet_b200 DefaultFrontend: single-channel (B, L) input only")
         lib.load()
@@ -111,11 +122,10 @@ class DefaultFrontend(torch.nn.Module):
         feats = torch.empty(B, Tf, self.n_mels, dtype=torch.float32, device=input.device)
         nblk = lib.load().espb_frontend_blocks(Tf)
         partial = torch.empty(B, nblk, self.n_mels, dtype=torch.float32, device=input.device)
-        call("espb_stft_logmel_f32", ptr(input), ptr(lens_dev), B, L, ptr(c["window"]), ptr(c["tw"]), ptr(c["start"]),
-             ptr(c["count"]), ptr(c["offset"]), ptr(c["weight"]), self.n_mels, ptr(feats), Tf, ptr(partial))
+        call("espb_stft_logmel_f32", ptr(input), ptr(lens_dev), B, L, self.hop_length, ptr(c["window"]), ptr(c["tw"]), ptr(c["twt"]), ptr(c["start"]),
+             ptr(c["count"]), ptr(c["offset"]), ptr(c["weight"]), c["nnz"], self.n_mels, ptr(feats), Tf, ptr(partial))
         _count()
-        _PARTIAL_SUMS.clear()
-        _PARTIAL_SUMS[feats.data_ptr()] = (partial, lens_dev)
+        feats._espb_partial = (partial, lens_dev, self.hop_length)
         feats_lens = torch.div(input_lengths, self.hop_length, rounding_mode="trunc") + 1
         return feats, feats_lens
 
@@ -135,10 +145,11 @@ class UtteranceMVN(torch.nn.Module):
         B, T, D = x.shape
         if ilens is None:
             ilens = torch.full((B,), T, dtype=torch.int64, device=x.device)
-        stash = _PARTIAL_SUMS.pop(x.data_ptr(), None)
+        stash = getattr(x, "_espb_partial", None)
         if stash is not None and x.is_contiguous():
-            partial, wave_lens = stash
-            call("espb_utt_mvn_from_partial_f32", ptr(x), ptr(wave_lens), B, T, D, ptr(partial))
+            partial, wave_lens, hop = stash
+            x._espb_partial = None                       # the sums describe the un-normalised features only
+            call("espb_utt_mvn_from_partial_f32", ptr(x), ptr(wave_lens), B, T, D, hop, ptr(partial))
             _count()
         else:
             x = x.contiguous()
@@ -174,7 +185,6 @@ class GlobalMVN(torch.nn.Module):
         B, T, D = x.shape
         if ilens is None:
             ilens = torch.full((B,), T, dtype=torch.int64, device=x.device)
-        _PARTIAL_SUMS.pop(x.data_ptr(), None)
         assert x.is_contiguous()
         lens_dev = ilens.to(device=x.device, dtype=torch.int64).contiguous()
         mean = self.mean.to(device=x.device, dtype=torch.float32).contiguous()

@@ -36,8 +36,8 @@ P, I, L, F = c_void_p, c_int, c_longlong, c_float
 # name -> argtypes (all return int status); mirrors include/espnet_b200.h
 _SIGS = {
     "espb_gemm_f32": [POINTER(GemmDesc), I, P],
-    "espb_stft_logmel_f32": [P, P, I, I, P, P, P, P, P, P, I, P, I, P, P],
-    "espb_utt_mvn_from_partial_f32": [P, P, I, I, I, P, P],
+    "espb_stft_logmel_f32": [P, P, I, I, I, P, P, P, P, P, P, P, I, I, P, I, P, P],
+    "espb_utt_mvn_from_partial_f32": [P, P, I, I, I, I, P, P],
     "espb_utt_mvn_f32": [P, P, I, I, I, P, P],
     "espb_global_mvn_f32": [P, P, I, I, I, P, P, I, I, P],
     "espb_layernorm_f32": [P, L, I, P, P, F, P, P, L, P],
@@ -72,7 +72,7 @@ _SIGS = {
     "espb_count_active_i32": [P, I, P, P],
 }
 
-ABI_VERSION = 4   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
+ABI_VERSION = 5   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["espb_last_error", "espb_abi_version", "espb_device_sm", "espb_frontend_blocks"])
 
 

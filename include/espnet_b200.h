@@ -60,11 +60,13 @@ int espb_gemm_f32(const EspbGemmDesc* d, int use_tc, cudaStream_t stream);
  * sparse form (start/count/offset per filter + packed weights); tw512[k] = (cos, -sin)(2 pi k / 512), k < 256.
  * partial [B][espb_frontend_blocks(Tf_max)][n_mels] receives per-block column sums for the MVN kernel (may be NULL). */
 int espb_frontend_blocks(int Tf_max);
-int espb_stft_logmel_f32(const float* wave, const long long* wave_lens, int B, int Lmax, const float* window, const float* tw512,
-                         const int* mel_start, const int* mel_count, const int* mel_offset, const float* mel_weight, int n_mels,
-                         float* out, int Tf_max, float* partial, cudaStream_t stream);
+/* hop: any hop length (Tf = 1 + len/hop); window: 512 taps (a shorter win_length is zero-padded around the centre by the caller, as torch.stft
+ * does); tw256t[k1*16 + n2] = (cos, -sin)(2 pi n2 k1 / 256), the twiddles of the 16 x 16 four-step FFT; mel_nnz = number of packed weights. */
+int espb_stft_logmel_f32(const float* wave, const long long* wave_lens, int B, int Lmax, int hop, const float* window, const float* tw512,
+                         const float* tw256t, const int* mel_start, const int* mel_count, const int* mel_offset, const float* mel_weight,
+                         int mel_nnz, int n_mels, float* out, int Tf_max, float* partial, cudaStream_t stream);
 /* UtteranceMVN.forward, norm_means only (espnet2/layers/utterance_mvn.py:45-88), in place. */
-int espb_utt_mvn_from_partial_f32(float* feats, const long long* wave_lens, int B, int Tf_max, int n_mels, const float* partial,
+int espb_utt_mvn_from_partial_f32(float* feats, const long long* wave_lens, int B, int Tf_max, int n_mels, int hop, const float* partial,
                                   cudaStream_t stream);
 int espb_utt_mvn_f32(float* feats, const long long* feat_lens, int B, int Tf_max, int n_mels, float* partial_ws, cudaStream_t stream);
 /* GlobalMVN.forward (espnet2/layers/global_mvn.py:74-103), in place: (x - mean) masked to the valid frames, then / std. */

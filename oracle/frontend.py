@@ -34,7 +34,7 @@ def slaney_mel_matrix(sr=16000, n_fft=512, n_mels=80, fmin=0.0, fmax=None):
     return torch.from_numpy(w.T.astype(np.float32).copy())
 
 
-def stft_power(wave, n_fft=512, hop=128):
+def stft_power(wave, n_fft=512, hop=128, win_length=None, window="hann"):
     """Stft.forward + power, one utterance.  espnet2/layers/stft.py:75-120 (torch.stft with
     center=True -> reflect pad n_fft//2, periodic hann(win=n_fft), onesided, normalized=False);
     power = re^2+im^2, espnet2/asr/frontend/default.py:110.   wave (L,) -> (T_f, n_fft/2+1),
@@ -44,7 +44,12 @@ def stft_power(wave, n_fft=512, hop=128):
     x = torch.nn.functional.pad(wave.view(1, 1, L), (pad, pad), mode="reflect").view(-1)
     n_frames = 1 + L // hop
     frames = x.unfold(0, n_fft, hop)[:n_frames]
-    win = torch.hann_window(n_fft, periodic=True, dtype=wave.dtype)
+    # window_func(win_length), periodic; torch.stft zero-pads it on both sides to n_fft (stft.py:84-93); window None = rectangular
+    win_length = n_fft if win_length is None else win_length
+    w = getattr(torch, f"{window}_window")(win_length, dtype=wave.dtype) if window is not None else torch.ones(win_length, dtype=wave.dtype)
+    left = (n_fft - win_length) // 2
+    win = torch.zeros(n_fft, dtype=wave.dtype)
+    win[left:left + win_length] = w
     spec = torch.fft.rfft(frames * win, dim=-1)
     return spec.real**2 + spec.imag**2
 

@@ -59,6 +59,17 @@ if which in ("srcattn", "all"):
     alg = 2 * U * H * T * 64 * 4
     timeit("dec_src_attn U64 H8 T937 W10", lambda: call("espb_dec_src_attn_f32", ptr(q), ptr(kv[0]), ptr(kv[1]), U, T, ptr(lens), W, D, H, ptr(ctx), n * D), alg)
 
+if which in ("frontend", "all"):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import espnet_b200
+
+    B, L = 64, 480000
+    fe = espnet_b200.DefaultFrontend().cuda()
+    wave = 0.1 * torch.randn(B, L, device=dev)
+    lens = torch.full((B,), L, dtype=torch.long)
+    alg = B * (4 * L + 320 * (1 + L // 128))
+    timeit("stft_logmel 64 x 30 s (algorithmic bytes: waveform read + log-mel write)", lambda: fe(wave, lens), alg)
+
 if which in ("selfattn", "all"):
     U, W, H, D, L = 64, 10, 8, 512, 64
     n = U * W

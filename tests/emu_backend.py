@@ -539,19 +539,19 @@ def install_search(monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ frontend / normalisation entry points
-def _stft_logmel(wave, lens, B, L, window, tw, start, count, offset, weight, n_mels, out, Tf, partial):
+def _stft_logmel(wave, lens, B, L, hop, window, tw, twt, start, count, offset, weight, nnz, n_mels, out, Tf, partial):
     """frontend.cu: torch.stft semantics per utterance (own reflect padding), power, SPARSE mel filterbank exactly as the tables describe it,
-    clamp 1e-10, log; frames >= 1 + len/128 are zero.  The per-block column sums go to block 0 (only their total is contractual)."""
+    clamp 1e-10, log; frames >= 1 + len/hop are zero (window: 512 taps, already zero-padded around the centre for win_length < 512).  The per-block column sums go to block 0 (only their total is contractual)."""
     o = out.view(B, Tf, n_mels)
     o.zero_()
     if partial is not None:
         partial.zero_()
     for b in range(B):
         n = int(lens[b])
-        spec = torch.stft(wave.view(B, L)[b, :n], 512, hop_length=128, win_length=512, window=window, center=True, pad_mode="reflect",
+        spec = torch.stft(wave.view(B, L)[b, :n], 512, hop_length=hop, win_length=512, window=window, center=True, pad_mode="reflect",
                           normalized=False, onesided=True, return_complex=True)
         power = (spec.real ** 2 + spec.imag ** 2).t()          # [Tf_b][257]
-        tf_b = 1 + n // 128
+        tf_b = 1 + n // hop
         assert power.shape[0] == tf_b
         for j in range(n_mels):
             s, c, w0 = int(start[j]), int(count[j]), int(offset[j])
@@ -561,10 +561,10 @@ def _stft_logmel(wave, lens, B, L, window, tw, start, count, offset, weight, n_m
             partial.view(B, -1, n_mels)[b, 0] = o[b, :tf_b].sum(0)
 
 
-def _utt_mvn_from_partial(feats, wave_lens, B, Tf_max, n_mels, partial):
+def _utt_mvn_from_partial(feats, wave_lens, B, Tf_max, n_mels, hop, partial):
     f = feats.view(B, Tf_max, n_mels)
     for b in range(B):
-        tf_b = 1 + int(wave_lens[b]) // 128
+        tf_b = 1 + int(wave_lens[b]) // hop
         f[b, :tf_b] -= partial.view(B, -1, n_mels)[b].sum(0) / tf_b
 
 

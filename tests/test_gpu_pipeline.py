@@ -80,6 +80,32 @@ def test_frontend_and_mvn_vs_oracle(lens):
         assert e < 5e-4, f"mvn max abs err {e}"
 
 
+@pytest.mark.parametrize("hop,win_length,window", [(160, None, "hann"), (160, 400, "hann"), (100, 320, "hamming"), (75, 512, None), (256, 512, "hann")])
+def test_frontend_other_hop_and_window_vs_oracle(hop, win_length, window):
+    """hop_length / win_length / window generality of the fused kernel (e.g. the hop-160 Conformer recipe,
+    egs2/librispeech/asr1/conf/tuning/train_asr_conformer10_hop_length160.yaml:37-38): ragged batch against the oracle (= torch.stft)."""
+    import espnet_b200
+
+    fe, mvn = espnet_b200.DefaultFrontend(hop_length=hop, win_length=win_length, window=window).cuda(), espnet_b200.UtteranceMVN()
+    lens = [21000, 9001, 16000]
+    waves = [refbuild.waveform(30 + i, n) for i, n in enumerate(lens)]
+    batch = torch.zeros(len(lens), max(lens))
+    for i, w in enumerate(waves):
+        batch[i, : lens[i]] = w
+    feats, flens = fe(batch.cuda(), torch.tensor(lens))
+    assert flens.tolist() == [1 + n // hop for n in lens]
+    raw = feats.clone()
+    norm, _ = mvn(feats, flens)
+    melmat = fe.logmel.melmat.cpu()
+    for i, w in enumerate(waves):
+        ref = OF.log_mel(OF.stft_power(w, hop=hop, win_length=win_length, window=window), melmat)
+        tf = ref.shape[0]
+        e = _maxerr(raw[i, :tf], ref)
+        assert e < 5e-4, f"log-mel max abs err {e}"
+        assert (raw[i, tf:].abs().max().item() == 0) if tf < raw.shape[1] else True
+        assert _maxerr(norm[i, :tf], OF.utterance_mvn(ref)) < 5e-4
+
+
 def test_standalone_mvn_kernel():
     import espnet_b200
 

@@ -161,3 +161,23 @@ def test_lm_fusion_oracle_vs_reference_fixture(dn):
         for k, ref in zip(("decoder", "ctc", "lm"), z[f"dec:{dn}:{i}:scores"]):
             if not np.isnan(ref):
                 assert abs(h.scores[k] - ref) <= 1e-4 * max(1.0, abs(ref)), k
+
+
+@pytest.mark.parametrize("hop,win_length,window", [(160, None, "hann"), (160, 400, "hann"), (100, 320, "hamming"), (75, 512, None)])
+def test_oracle_stft_generalised_vs_torch_stft(hop, win_length, window):
+    """The oracle's framing for other hop / window settings (recipes such as train_asr_conformer10_hop_length160.yaml:37-38) is torch.stft's, the
+    call the reference makes (espnet2/layers/stft.py:94-105)."""
+    import torch
+
+    from oracle import frontend as OF
+
+    g = torch.Generator().manual_seed(hop)
+    wave = torch.randn(7000, generator=g)
+    wl = 512 if win_length is None else win_length
+    w = getattr(torch, f"{window}_window")(wl) if window is not None else None
+    spec = torch.stft(wave, 512, hop_length=hop, win_length=wl, window=w, center=True, pad_mode="reflect", normalized=False, onesided=True,
+                      return_complex=True)
+    ref = (spec.real ** 2 + spec.imag ** 2).t()
+    got = OF.stft_power(wave, hop=hop, win_length=win_length, window=window)
+    assert got.shape == ref.shape == (1 + 7000 // hop, 257)
+    assert float((got - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
