@@ -154,6 +154,18 @@ class Speech2Text:
         self.tokenizer = tokenizer_for_inference(token_type, bpemodel, asr_train_args)   # asr_inference.py:395-430
         logger.info(f"Text tokenizer: {self.tokenizer}")
 
+    @staticmethod
+    def from_pretrained(model_tag: Optional[str] = None, **kwargs):
+        """asr_inference.py:680-707: with a model tag the files come from espnet_model_zoo (must be installed, as for the reference)."""
+        if model_tag is not None:
+            try:
+                from espnet_model_zoo.downloader import ModelDownloader
+            except ImportError:
+                logger.error("`espnet_model_zoo` is not installed. Please install via `pip install -U espnet_model_zoo`.")
+                raise
+            kwargs.update(**ModelDownloader().download_and_unpack(model_tag))
+        return Speech2Text(**kwargs)
+
     def _to_batch(self, speeches: Sequence[Union[torch.Tensor, np.ndarray]]):
         lens = torch.tensor([int(s.shape[0]) for s in speeches], dtype=torch.long)
         L = int(lens.max())

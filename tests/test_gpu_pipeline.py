@@ -377,3 +377,31 @@ def test_utterance_groups_on_streams_match_single_group(groups):
     for i in (0, 4, 6):
         ref = o(waves[i])
         assert [h[3].yseq.tolist() for h in grouped[i]] == [h[3].yseq.tolist() for h in ref]
+
+
+def test_cli_inference_writes_reference_style_result_dir(tmp_path):
+    """espnet_b200.bin_asr_inference.inference (asr_inference.py:711-906): wav.scp in, {n}best_recog/{token,token_int,score} out, batch 2,
+    a too-short utterance replaced by the reference's placeholder; tokens equal the direct API's."""
+    import wave as wavmod
+
+    from espnet_b200.bin_asr_inference import inference
+
+    z, cfg, w = load("tiny")
+    s2t = speech2text(cfg, w, beam_size=3, ctc_weight=0.3, maxlenratio=-6.0, nbest=2)
+    lines = []
+    waves = {"a": refbuild.waveform(1, 9000), "b": refbuild.waveform(2, 12000), "short": torch.zeros(600), "c": refbuild.waveform(3, 8000)}
+    for k, x in waves.items():
+        pcm = (x.clamp(-1, 1) * 32767).round().to(torch.int16).numpy()
+        with wavmod.open(str(tmp_path / f"{k}.wav"), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(pcm.tobytes())
+        lines.append(f"{k} {tmp_path / (k + '.wav')}")
+        waves[k] = torch.from_numpy(pcm.astype("float32") / 32768.0)
+    (tmp_path / "wav.scp").write_text("\n".join(lines) + "\n")
+    out = inference(str(tmp_path / "decode"), [(str(tmp_path / "wav.scp"), "speech", "sound")], batch_size=2, nbest=2, speech2text=s2t)
+    tok = dict(ln.split(maxsplit=1) if " " in ln.strip() else (ln.strip(), "") for ln in (tmp_path / "decode/1best_recog/token_int").read_text().splitlines())
+    assert set(tok) == {"a", "b", "short", "c"} and tok["short"].strip() == "2"
+    for k in ("a", "b", "c"):
+        ref = s2t(waves[k])
+        assert tok[k].split() == [str(t) for t in ref[0][2]]
+        assert out[k][0][3].yseq.tolist() == ref[0][3].yseq.tolist()
+    assert (tmp_path / "decode/2best_recog/score").exists()

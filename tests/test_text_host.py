@@ -103,3 +103,36 @@ def test_speech2text_refuses_unimplemented_reference_keywords():
     with pytest.raises(Exception) as e:
         espnet_b200.Speech2Text(asr_model=None, asr_train_config=None, lm_file=None, streaming=False, quantize_modules=["Linear"], device="cpu")
     assert "does not implement" not in str(e.value)
+
+
+def test_result_dir_writer_and_scp_reader(tmp_path):
+    """The result directory of the CLI (asr_inference.py:884-896 through DatadirWriter semantics) and the wav.scp / key_file / rank sharding."""
+    import wave
+
+    import numpy as np
+    import torch
+
+    from espnet_b200.bin_asr_inference import ResultDirWriter, iter_scp, read_sound, write_results
+    from espnet_b200.search import Hypothesis
+
+    with ResultDirWriter(tmp_path / "out") as w:
+        for key, toks in (("utt1", [3, 4]), ("utt2", [5])):
+            res = [("t e", [f"t{t}" for t in toks], toks, Hypothesis(yseq=torch.tensor([9] + toks + [9]), score=-1.5))]
+            write_results(w, key, res, nbest=1)
+        with pytest.raises(RuntimeError):
+            w["1best_recog"]["x"] = "a directory cannot be assigned"
+    assert (tmp_path / "out/1best_recog/token").read_text() == "utt1 t3 t4\nutt2 t5\n"
+    assert (tmp_path / "out/1best_recog/token_int").read_text() == "utt1 3 4\nutt2 5\n"
+    assert (tmp_path / "out/1best_recog/score").read_text() == "utt1 -1.5\nutt2 -1.5\n"
+    assert (tmp_path / "out/1best_recog/text").read_text() == "utt1 t e\nutt2 t e\n"
+    x = (np.sin(np.arange(1600) / 10.0) * 20000).astype("<i2")
+    with wave.open(str(tmp_path / "a.wav"), "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(x.tobytes())
+    np.save(tmp_path / "b.npy", np.ones(10, dtype=np.float32))
+    (tmp_path / "wav.scp").write_text(f"u1 {tmp_path / 'a.wav'}\nu2 {tmp_path / 'b.npy'}\nu3 {tmp_path / 'a.wav'}\n")
+    (tmp_path / "keys").write_text("u1\nu3 something\n")
+    assert [k for k, _ in iter_scp(str(tmp_path / "wav.scp"))] == ["u1", "u2", "u3"]
+    assert [k for k, _ in iter_scp(str(tmp_path / "wav.scp"), str(tmp_path / "keys"))] == ["u1", "u3"]
+    assert [k for k, _ in iter_scp(str(tmp_path / "wav.scp"), None, rank=1, world=2)] == ["u2"]
+    np.testing.assert_allclose(read_sound(str(tmp_path / "a.wav")), x.astype(np.float32) / 32768.0)
+    assert read_sound(str(tmp_path / "b.npy")).shape == (10,)
