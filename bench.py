@@ -36,6 +36,9 @@ WORKLOADS = {
                                        30, 64, 5, 0.0, -64.0),
 }
 METRIC = "utterances/sec (RTF) Conformer-large ASR inference at 1/2/4/8 B200 vs CPU ref"
+# BASELINE.json configs[3] (next row 8f-2): contextual-block Conformer (12L/512d/8h, block 40 / hop 16 / look-ahead 16), 128 live streams per GPU,
+# 40-ms pushes (640 samples).  One "step" = 64 pushes (2.56 s of audio per stream); value = audio seconds processed per second (all streams).
+STREAMING = {"streaming_cbconformer_128x40ms": dict(streams=128, push=640, pushes_per_step=64, d_model=512, heads=8, ff=2048, layers=12, vocab=5000)}
 
 
 def waveforms(n, nsamples, offset=0):
@@ -270,6 +273,72 @@ def run_reference(args, rank, world):
 NCU_TRAFFIC = {"launch": "gemm_tf32x3_2cta_kernel<256,3,swish,split> M59968 N2048 K512", "dram_bytes": 275.803136e6 + 959.088128e6,
                "algorithmic_bytes": (2 * 59968 * 512 + 2 * 2048 * 512 + 2 * 59968 * 2048) * 4.0, "gpu_time_us_under_ncu": 627.264,
                "tensor_pipe_active_pct": 61.13, "source": "profiles/r01_ncu_gemm_2cta_ffn_w1_summary.txt"}
+
+
+def run_streaming(args, rank, local_rank, world):
+    """Streaming workload: frontend chunking -> ContextualBlockConformerEncoder.forward_infer -> CTC greedy, N streams in lock step."""
+    import argparse as _ap
+
+    import torch.distributed as dist
+
+    import espnet_b200
+    from espnet_b200 import ops
+    from gpu_util import refbuild
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    w = STREAMING[args.workload]
+    y = refbuild.model_yaml(dict(d_model=w["d_model"], heads=w["heads"], ff=w["ff"], enc_layers=w["layers"], dec_layers=1, vocab=w["vocab"], kernel=31))
+    y.update(encoder="contextual_block_conformer", normalize=None, normalize_conf={}, decoder=None,
+             encoder_conf=dict(output_size=w["d_model"], attention_heads=w["heads"], linear_units=w["ff"], num_blocks=w["layers"], macaron_style=True,
+                               cnn_module_kernel=31, block_size=40, hop_size=16, look_ahead=16))
+    torch.manual_seed(0)
+    model = espnet_b200.build_model(_ap.Namespace(**y)).to(dev).eval()
+    s2t = espnet_b200.Speech2TextStreaming(model, n_streams=w["streams"], device=str(dev))
+    host = waveforms(w["streams"], w["push"] * w["pushes_per_step"], offset=rank * w["streams"]).pin_memory()
+
+    def step():
+        n_tok = 0
+        for p in range(w["pushes_per_step"]):
+            new = s2t(host[:, p * w["push"]:(p + 1) * w["push"]], is_final=False)     # pinned host chunk -> device inside the call
+            n_tok += sum(len(t) for t in new)
+        return n_tok
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier(); sampler.start(); ops.launch_counter[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank != 0:
+        return
+    audio_s = world * w["streams"] * w["pushes_per_step"] * args.steps * w["push"] / 16000.0
+    val = audio_s / (ms / 1000.0)
+    line = {"metric": "audio seconds per second, streaming contextual-block Conformer + CTC greedy (BASELINE configs[3] shape)", "value": val,
+            "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "streams_per_gpu": w["streams"], "push_ms": 1000.0 * w["push"] / 16000.0,
+                       "pushes_per_step": w["pushes_per_step"], "real_time_streams_sustained": val, "ms_per_push": ms / args.steps / w["pushes_per_step"],
+                       "model": "contextual-block Conformer 12L/512d/8h block 40 hop 16 look-ahead 16, V=5000, CTC greedy",
+                       "note": "next-row workload (SURVEY 8f-2): host chunks are copied inside the timed region; no beam search"},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": w["streams"] * w["push"] * w["pushes_per_step"] * 4, "d2h_bytes_per_step": 0},
+            "gpu_launches": ops.launch_counter[0], "clocks": clocks}
+    print(json.dumps(line), flush=True)
 
 
 def run_b200(args, rank, local_rank, world):
@@ -512,7 +581,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="conformer_large_joint_64x30s", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="conformer_large_joint_64x30s", choices=sorted(WORKLOADS) + sorted(STREAMING))
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--trace", action="store_true", help="CUPTI activity trace of one step (kernel durations inside the CUDA graphs) -> stderr")
     ap.add_argument("--breakdown", action="store_true", help="time every launch of one step with CUDA events and print a per-kernel table")
@@ -528,7 +597,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_b200(args, rank, local_rank, world)
+        (run_streaming if args.workload in STREAMING else run_b200)(args, rank, local_rank, world)
     finally:
         if world > 1:
             import torch.distributed as dist

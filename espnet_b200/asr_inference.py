@@ -32,7 +32,9 @@ logger = logging.getLogger(__name__)
 # name -> class registries, as espnet2/tasks/asr.py:95-206 (only the classes on the north-star path)
 frontend_choices = {"default": DefaultFrontend}
 normalize_choices = {"global_mvn": GlobalMVN, "utterance_mvn": UtteranceMVN}
-encoder_choices = {"conformer": ConformerEncoder, "transformer": TransformerEncoder}
+from .streaming_encoder import ContextualBlockConformerEncoder  # noqa: E402
+
+encoder_choices = {"conformer": ConformerEncoder, "transformer": TransformerEncoder, "contextual_block_conformer": ContextualBlockConformerEncoder}
 decoder_choices = {"transformer": TransformerDecoder}
 
 

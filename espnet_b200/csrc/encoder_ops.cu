@@ -376,9 +376,111 @@ __global__ void zero_pad_rows_kernel(float* __restrict__ x, int Tmax, int D, con
   }
 }
 
+// ---------------------------------------------------------------- contextual block processing (streaming encoder)
+// contextual_block_conformer_encoder.py:506-541: blocks of `block` frames every `hop` frames, framed by two context tokens:
+//   chunk[n][i][0]          = context vector of the previous block (or of the previous call / of this block for the very first one)
+//   chunk[n][i][1..len]     = pos_enc(xs[n][i*hop + t], start pos0 + i*hop)        (StreamPositionalEncoding: x * sqrt(D) + pe[pos])
+//   chunk[n][i][block+1]    = addin_i = pos_enc(mean_t xs[n][i*hop .. +len), start ctx0 + i)
+// rows len+1..block of a trailing partial block stay zero.
+__global__ void __launch_bounds__(128) cbe_build_chunks_kernel(const float* __restrict__ xs, int Tt, int D, int nb, int block, int hop,
+                                                               const float* __restrict__ pe, int pos0, int ctx0, float scale,
+                                                               const float* __restrict__ prev_addin, float* __restrict__ addin_out,
+                                                               float* __restrict__ chunks) {
+  const int i = blockIdx.x, n = blockIdx.y, S = block + 2;
+  const float* x = xs + (long long)n * Tt * D;
+  float* c = chunks + ((long long)n * nb + i) * S * D;
+  const int cur = i * hop, len = min(block, Tt - cur);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float sum = 0.f;
+    for (int t = 0; t < len; ++t) {
+      const float v = x[(long long)(cur + t) * D + d];
+      sum += v;
+      c[(long long)(1 + t) * D + d] = v * scale + pe[(long long)(pos0 + cur + t) * D + d];
+    }
+    for (int t = len; t < block; ++t) c[(long long)(1 + t) * D + d] = 0.f;
+    const float addin = (sum / (float)len) * scale + pe[(long long)(ctx0 + i) * D + d];
+    c[(long long)(block + 1) * D + d] = addin;
+    float prev;
+    if (i > 0) {
+      const int pc = (i - 1) * hop, pl = min(block, Tt - pc);
+      float ps = 0.f;
+      for (int t = 0; t < pl; ++t) ps += x[(long long)(pc + t) * D + d];
+      prev = (ps / (float)pl) * scale + pe[(long long)(ctx0 + i - 1) * D + d];
+    } else {
+      prev = prev_addin ? prev_addin[(long long)n * D + d] : addin;
+    }
+    c[d] = prev;
+    if (i == nb - 1) addin_out[(long long)n * D + d] = addin;
+  }
+}
+
+// contextual_block_encoder_layer.py:291-308: after a layer, token 0 of every block becomes the previous block's last token (the context
+// inherited from the layer below it in time); the first block takes the context kept from the previous call; the last one is kept.
+__global__ void __launch_bounds__(128) cbe_ctx_propagate_kernel(float* __restrict__ x, int nb, int S, int D, const float* __restrict__ past_ctx,
+                                                                float* __restrict__ next_ctx, int layer, int L) {
+  const int i = blockIdx.x, n = blockIdx.y;
+  float* xb = x + ((long long)n * nb + i) * S * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float v;
+    if (i > 0) v = xb[-(long long)S * D + (long long)(S - 1) * D + d];                   // last token of block i-1
+    else v = past_ctx ? past_ctx[((long long)n * L + layer) * D + d] : xb[(long long)(S - 1) * D + d];
+    if (i == nb - 1) next_ctx[((long long)n * L + layer) * D + d] = xb[(long long)(S - 1) * D + d];
+    xb[d] = v;          // token 0; every value read above is a LAST token, which nobody writes
+  }
+}
+
+// rows row0 + k * every (k < count) of a [rows][D] buffer (nplanes planes) := 0
+__global__ void zero_rows_kernel(float* __restrict__ x, long long row0, long long every, long long count, int D, long long plane, int nplanes) {
+  const long long k = blockIdx.x;
+  if (k >= count) return;
+  float* r = x + (row0 + k * every) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x)
+    for (int q = 0; q < nplanes; ++q) r[q * plane + d] = 0.f;
+}
+
+// out[n][t][:] = src[n][idx[t]][:]
+__global__ void gather_rows_kernel(const float* __restrict__ src, long long src_rows, const int* __restrict__ idx, int nout, int D,
+                                   float* __restrict__ out) {
+  const int t = blockIdx.x, n = blockIdx.y;
+  const float* s = src + ((long long)n * src_rows + idx[t]) * D;
+  float* o = out + ((long long)n * nout + t) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) o[d] = s[d];
+}
+
 }  // namespace
 
 extern "C" {
+
+int espb_cbe_build_chunks_f32(const float* xs, int N, int Tt, int D, int nb, int block, int hop, const float* pe, int pos0, int ctx0, float scale,
+                              const float* prev_addin, float* addin_out, float* chunks, cudaStream_t stream) {
+  if (N <= 0 || nb <= 0 || block <= 0 || hop <= 0 || (nb - 1) * hop >= Tt) { espb_set_error("cbe_build_chunks: bad shape"); return ESPB_ERR_ARG; }
+  cbe_build_chunks_kernel<<<dim3(nb, N), 128, 0, stream>>>(xs, Tt, D, nb, block, hop, pe, pos0, ctx0, scale, prev_addin, addin_out, chunks);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_cbe_ctx_propagate_f32(float* x, int N, int nb, int S, int D, const float* past_ctx, float* next_ctx, int layer, int L,
+                               cudaStream_t stream) {
+  if (N <= 0 || nb <= 0) return ESPB_OK;
+  // block i reads the last token of block i-1, which no block writes (only tokens 0 are written): one launch is race-free
+  cbe_ctx_propagate_kernel<<<dim3(nb, N), 128, 0, stream>>>(x, nb, S, D, past_ctx, next_ctx, layer, L);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_zero_rows_f32(float* x, long long row0, long long every, long long count, int D, long long plane, int nplanes, cudaStream_t stream) {
+  if (count <= 0) return ESPB_OK;
+  zero_rows_kernel<<<(unsigned)count, 128, 0, stream>>>(x, row0, every, count, D, plane, nplanes);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_gather_rows_f32(const float* src, int N, long long src_rows, const int* idx, int nout, int D, float* out, cudaStream_t stream) {
+  if (N <= 0 || nout <= 0) return ESPB_OK;
+  gather_rows_kernel<<<dim3(nout, N), 128, 0, stream>>>(src, src_rows, idx, nout, D, out);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
 
 int espb_layernorm_f32(const float* x, long long rows, int D, const float* gamma, const float* beta, float eps, float* out_plain,
                        float* out_split, long long split_plane, cudaStream_t stream) {

@@ -50,6 +50,10 @@ _SIGS = {
     "espb_flash_attn_f32": [P, L, L, L, P, L, L, L, P, L, I, P, I, P, I, I, I, I, P, L, L, P],
     "espb_glu_dwconv_bn_swish_f32": [P, I, I, I, P, P, P, I, P, P, P, L, P],
     "espb_zero_pad_rows_f32": [P, I, I, I, P, L, I, P],
+    "espb_cbe_build_chunks_f32": [P, I, I, I, I, I, I, P, I, I, F, P, P, P, P],
+    "espb_cbe_ctx_propagate_f32": [P, I, I, I, I, P, P, I, I, P],
+    "espb_zero_rows_f32": [P, L, L, L, I, L, I, P],
+    "espb_gather_rows_f32": [P, I, L, P, I, I, P, P],
     "espb_log_softmax_rows_f32": [P, L, L, I, P],
     "espb_argmax_rows_f32": [P, L, L, I, P, P],
     "espb_ctc_collapse_i32": [P, I, I, P, I, P, P, P],
@@ -72,7 +76,7 @@ _SIGS = {
     "espb_count_active_i32": [P, I, P, P],
 }
 
-ABI_VERSION = 5   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
+ABI_VERSION = 6   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["espb_last_error", "espb_abi_version", "espb_device_sm", "espb_frontend_blocks"])
 
 

@@ -108,6 +108,17 @@ int espb_glu_dwconv_bn_swish_f32(const float* y, int B, int Tmax, int C, const i
                                  const float* bn_a, const float* bn_b, float* out, long long out_plane, cudaStream_t stream);
 int espb_zero_pad_rows_f32(float* x, int B, int Tmax, int D, const int* lens, long long plane, int nplanes, cudaStream_t stream);
 
+/* ---- streaming encoder: contextual block processing (espnet2/asr/encoder/contextual_block_conformer_encoder.py:506-572,
+ *      legacy/nets/pytorch_backend/conformer/contextual_block_encoder_layer.py:291-308) ---- */
+/* chunks [N][nb][block+2][D] from the subsampled frames xs [N][Tt][D]: context token | pos_enc(frames) | context of this block */
+int espb_cbe_build_chunks_f32(const float* xs, int N, int Tt, int D, int nb, int block, int hop, const float* pe, int pos0, int ctx0, float scale,
+                              const float* prev_addin, float* addin_out, float* chunks, cudaStream_t stream);
+/* token 0 of block i := last token of block i-1 (block 0: past_ctx[n][layer] or its own last token); next_ctx[n][layer] := last token of the last block */
+int espb_cbe_ctx_propagate_f32(float* x, int N, int nb, int S, int D, const float* past_ctx, float* next_ctx, int layer, int L,
+                               cudaStream_t stream);
+int espb_zero_rows_f32(float* x, long long row0, long long every, long long count, int D, long long plane, int nplanes, cudaStream_t stream);
+int espb_gather_rows_f32(const float* src, int N, long long src_rows, const int* idx, int nout, int D, float* out, cudaStream_t stream);
+
 /* ---- CTC head (espnet2/asr/ctc.py:197-215; greedy collapse asr_inference.py:574-575, s2t_inference_ctc.py:630-632) ---- */
 int espb_log_softmax_rows_f32(float* x, long long rows, long long ld, int V, cudaStream_t stream);
 int espb_argmax_rows_f32(const float* x, long long rows, long long ld, int V, int* out, cudaStream_t stream);

@@ -184,7 +184,48 @@ def _glu_dwconv_bn_swish(y, B, Tmax, C, lens, dw_w, dw_b, K, bn_a, bn_b, out, ou
     _store(_flat(out), torch.arange(B * Tmax * C).view(B, Tmax, C), z, True, out_plane)
 
 
-_TABLE = {"espb_split_tf32_f32": _split_tf32, "espb_layernorm_f32": _layernorm, "espb_conv1_relu_f32": _conv1_relu, "espb_qu_qv_f32": _qu_qv,
+def _cbe_build_chunks(xs, N, Tt, D, nb, block, hop, pe, pos0, ctx0, scale, prev_addin, addin_out, chunks):
+    x = _flat(xs)[: N * Tt * D].view(N, Tt, D)
+    c = chunks.view(N, nb, block + 2, D)
+    c.zero_()
+    pev = pe.view(-1, D)
+    sc = torch.tensor(scale, dtype=torch.float32)
+    prev = prev_addin.view(N, D).clone() if prev_addin is not None else None
+    for i in range(nb):
+        cur = i * hop
+        ln = min(block, Tt - cur)
+        seg = x[:, cur:cur + ln]
+        addin = (seg.sum(1) / ln) * sc + pev[ctx0 + i]
+        c[:, i, 1:ln + 1] = seg * sc + pev[pos0 + cur: pos0 + cur + ln]
+        c[:, i, block + 1] = addin
+        c[:, i, 0] = addin if prev is None else prev
+        prev = addin
+    addin_out.view(N, D).copy_(prev)
+
+
+def _cbe_ctx_propagate(x, N, nb, S, D, past_ctx, next_ctx, layer, L):
+    xv = x.view(N, nb, S, D)
+    last = xv[:, :, S - 1].clone()
+    next_ctx.view(N, L, D)[:, layer] = last[:, nb - 1]
+    xv[:, 0, 0] = past_ctx.view(N, L, D)[:, layer] if past_ctx is not None else last[:, 0]
+    if nb > 1:
+        xv[:, 1:, 0] = last[:, :-1]
+
+
+def _zero_rows(x, row0, every, count, D, plane, nplanes):
+    f = _flat(x)
+    for q in range(nplanes):
+        for k in range(count):
+            o = q * plane + (row0 + k * every) * D
+            f[o:o + D] = 0.0
+
+
+def _gather_rows(src, N, src_rows, idx, nout, D, out):
+    out.view(N, nout, D).copy_(_flat(src)[: N * src_rows * D].view(N, src_rows, D)[:, idx.view(-1)[:nout].long()])
+
+
+_TABLE = {"espb_cbe_build_chunks_f32": _cbe_build_chunks, "espb_cbe_ctx_propagate_f32": _cbe_ctx_propagate, "espb_zero_rows_f32": _zero_rows,
+          "espb_gather_rows_f32": _gather_rows, "espb_split_tf32_f32": _split_tf32, "espb_layernorm_f32": _layernorm, "espb_conv1_relu_f32": _conv1_relu, "espb_qu_qv_f32": _qu_qv,
           "espb_v_transpose_f32": _v_transpose, "espb_relpos_softmax_f32": _relpos_softmax, "espb_masked_softmax_f32": _masked_softmax,
           "espb_flash_attn_f32": _flash_attn, "espb_glu_dwconv_bn_swish_f32": _glu_dwconv_bn_swish}
 calls = []   # names of the emulated entry points, in call order (tests can assert on the sequence)
@@ -201,10 +242,12 @@ def install(monkeypatch):
     """Route the encoder-side modules of espnet_b200 through the emulation (CPU tensors)."""
     import espnet_b200.encoder as enc
     import espnet_b200.ops as ops
+    import espnet_b200.streaming_encoder as senc
     import espnet_b200.transformer_encoder as tenc
 
     del calls[:]
-    for mod in (ops, enc, tenc):
+    monkeypatch.setattr(senc, "gemm", gemm, raising=True)
+    for mod in (ops, enc, tenc, senc):
         monkeypatch.setattr(mod, "call", call, raising=True)
         monkeypatch.setattr(mod, "ptr", ptr, raising=True)
     monkeypatch.setattr(ops, "gemm", gemm, raising=True)
