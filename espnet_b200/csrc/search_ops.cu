@@ -836,22 +836,24 @@ struct BeamState {
 // mode 1: joint             -- candidates j<P from the pre-beam + eos as candidate P; part/valid [n][P+1]
 //                              total = ((dec + penalty) + w_ctc*part) + score   (batch_beam_search.py:293-309)
 // mode 2: CTC only (dense)  -- cand_val[n][P] = w_ctc*part of cand_ids, part = dense [n][V]
-template <int MAXC>   // each lane owns candidates lane, lane+32, ...: supports W*PC <= 32*MAXC
-__global__ void __launch_bounds__(32) beam_select_kernel(BeamState st, int U, int W, int P, int V, int step, const int* __restrict__ step_ptr,
+template <int MAXC, int NT>   // each thread owns candidates tid, tid+NT, ...: supports W*PC <= NT*MAXC; NT = 32 (one warp) or 256 (wide beams)
+__global__ void __launch_bounds__(NT) beam_select_kernel(BeamState st, int U, int W, int P, int V, int step, const int* __restrict__ step_ptr,
                                                          const int* __restrict__ maxlen,
                                                          const int* __restrict__ minlen, int eos, float w_dec, float w_ctc, float penalty, int mode,
                                                          const int* __restrict__ cand_ids, const float* __restrict__ cand_val,
                                                          const float* __restrict__ logp_dec /* [n][V] or null */, const float* __restrict__ part,
                                                          const int* __restrict__ valid, int end_detect, int maxlen_cap) {
   if (step_ptr) step += *step_ptr;
-  const int u = blockIdx.x, lane = threadIdx.x;
+  const int u = blockIdx.x, lane = threadIdx.x;   // `lane`: thread index within the block (a warp for NT = 32)
+  __shared__ float red_v[NT / 32];
+  __shared__ int red_i[NT / 32];
   const int PC = (mode == 1) ? P + 1 : P;   // candidates per slot
   const int total = W * PC;
   float tot[MAXC];
   const bool done = st.utt_done[u] != 0;
 #pragma unroll
   for (int q = 0; q < MAXC; ++q) {
-    const int ci = lane + q * 32;
+    const int ci = lane + q * NT;
     float t = -INFINITY;
     if (ci < total && !done) {
       const int w = ci / PC, j = ci % PC, s = u * W + w;
@@ -876,7 +878,7 @@ __global__ void __launch_bounds__(32) beam_select_kernel(BeamState st, int U, in
     float best = -INFINITY; int bidx = 0x7fffffff;
 #pragma unroll
     for (int q = 0; q < MAXC; ++q) {
-      const int ci = lane + q * 32;
+      const int ci = lane + q * NT;
       if (tot[q] > best) { best = tot[q]; bidx = ci; }
     }
 #pragma unroll
@@ -884,6 +886,17 @@ __global__ void __launch_bounds__(32) beam_select_kernel(BeamState st, int U, in
       const float ov = __shfl_xor_sync(0xffffffffu, best, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
       if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    if (NT > 32) {   // across the warps of the block: every thread ends up with the same winner
+      __syncthreads();
+      if ((lane & 31) == 0) { red_v[lane >> 5] = best; red_i[lane >> 5] = bidx; }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) {
+        const float ov = red_v[w];
+        const int oi = red_i[w];
+        if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+      }
     }
     const int ns = u * W + k;
     const long long bp = (long long)step * U * W + ns;
@@ -895,7 +908,7 @@ __global__ void __launch_bounds__(32) beam_select_kernel(BeamState st, int U, in
       continue;
     }
 #pragma unroll
-    for (int q = 0; q < MAXC; ++q) if (lane + q * 32 == bidx) tot[q] = -INFINITY;   // remove the winner
+    for (int q = 0; q < MAXC; ++q) if (lane + q * NT == bidx) tot[q] = -INFINITY;   // remove the winner
     if (lane == 0) {
       const int w = bidx / PC, j = bidx % PC, s = u * W + w;
       const int tok = (mode == 1 && j == P) ? eos : cand_ids[(long long)s * P + j];
@@ -1185,7 +1198,7 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
 }
 
 int espb_rows_topk_f32(const float* x, long long rows, long long ld, int V, float scale, int k, int* ids, float* vals, cudaStream_t stream) {
-  if (k > 64 || k > V || V > 256 * 128) { espb_set_error("rows_topk: k must be <= min(64, V) and V <= 32768"); return ESPB_ERR_ARG; }
+  if (k > 128 || k > V || V > 256 * 128) { espb_set_error("rows_topk: k must be <= min(128, V) and V <= 32768"); return ESPB_ERR_ARG; }
   if (V <= 256 * 4) rows_topk_kernel<4><<<(unsigned)rows, 256, 0, stream>>>(x, ld, V, scale, k, ids, vals);
   else if (V <= 256 * 20) rows_topk_kernel<20><<<(unsigned)rows, 256, 0, stream>>>(x, ld, V, scale, k, ids, vals);
   else if (V <= 256 * 40) rows_topk_kernel<40><<<(unsigned)rows, 256, 0, stream>>>(x, ld, V, scale, k, ids, vals);
@@ -1229,17 +1242,19 @@ int espb_beam_select(const float* score, const float* sc_dec, const float* sc_ct
                      float w_dec, float w_ctc, float penalty, int mode, const int* cand_ids, const float* cand_val, const float* logp_dec,
                      const float* part, const int* valid, int end_detect, int maxlen_cap, cudaStream_t stream) {
   const int PC = (mode == 1) ? P + 1 : P;
-  if (W * PC > 1664 || W > 32 || mode < 0 || mode > 2) { espb_set_error("beam_select: beam * candidates > 1664 or bad mode"); return ESPB_ERR_ARG; }
+  if (W * PC > 256 * 28 || W > 64 || mode < 0 || mode > 2) { espb_set_error("beam_select: beam > 64, beam * candidates > 7168 or bad mode"); return ESPB_ERR_ARG; }
   BeamState st{score, sc_dec, sc_ctc, active, n_score, n_sc_dec, n_sc_ctc, n_active, n_last_tok, n_parent, bp_parent, bp_token,
                ended_count, ended_step, ended_slot, ended_score, ended_dec, ended_ctc, ended_cap, best_at_step, best_all, utt_done};
-#define ESPB_BEAM_SELECT(MC)                                                                                                                     \
-  beam_select_kernel<MC><<<U, 32, 0, stream>>>(st, U, W, P, V, step, step_ptr, maxlen, minlen, eos, w_dec, w_ctc, penalty, mode, cand_ids, cand_val, \
-                                               logp_dec, part, valid, end_detect, maxlen_cap)
+#define ESPB_BEAM_SELECT(MC, NT)                                                                                                                       \
+  beam_select_kernel<MC, NT><<<U, NT, 0, stream>>>(st, U, W, P, V, step, step_ptr, maxlen, minlen, eos, w_dec, w_ctc, penalty, mode, cand_ids, cand_val, \
+                                                   logp_dec, part, valid, end_detect, maxlen_cap)
   const int total = W * PC;
-  if (total <= 32 * 6) ESPB_BEAM_SELECT(6);
-  else if (total <= 32 * 12) ESPB_BEAM_SELECT(12);
-  else if (total <= 32 * 24) ESPB_BEAM_SELECT(24);
-  else ESPB_BEAM_SELECT(52);
+  if (total <= 32 * 6) ESPB_BEAM_SELECT(6, 32);
+  else if (total <= 32 * 12) ESPB_BEAM_SELECT(12, 32);
+  else if (total <= 32 * 24) ESPB_BEAM_SELECT(24, 32);
+  else if (total <= 32 * 52 && W <= 32) ESPB_BEAM_SELECT(52, 32);
+  else if (total <= 256 * 14) ESPB_BEAM_SELECT(14, 256);      // wide beams (the reference's Librispeech decode_asr.yaml: beam 60, pre-beam 90)
+  else ESPB_BEAM_SELECT(28, 256);
 #undef ESPB_BEAM_SELECT
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;

@@ -63,8 +63,8 @@ class BatchBeamSearch(torch.nn.Module):
         self.normalize_length = normalize_length
         self.full_scorers = {k: v for k, v in (("decoder", self.decoder), ("lm", self.lm)) if v is not None}
         self.part_scorers = {k: v for k, v in (("ctc", self.ctc),) if v is not None}
-        if beam_size > 32:
-            raise NotImplementedError("beam_size > 32 (the per-utterance beam selection runs in one warp)")
+        if beam_size > 64:
+            raise NotImplementedError("beam_size > 64 (beam selection: one block per utterance, 64 slots; cross-attention: groups of 16 slots up to 64)")
 
     # ---------------------------------------------------------------- search state (cached per shape so that CUDA graphs can be reused)
     def _state(self, dev, U, Tmax, W, V, cap, mode, P, g=0, end_detect=0):

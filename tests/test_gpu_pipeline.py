@@ -292,10 +292,29 @@ def test_wide_beam_vs_oracle(heads, beam, ctc_weight):
             assert abs(a[3].score - b[3].score) <= 2e-4 * max(1.0, abs(b[3].score))
 
 
-def test_beam_wider_than_32_is_refused():
+def test_beam_wider_than_64_is_refused():
     z, cfg, w = load("tiny")
     with pytest.raises(NotImplementedError):
-        speech2text(cfg, w, beam_size=33, ctc_weight=0.3)
+        speech2text(cfg, w, beam_size=65, ctc_weight=0.3)
+
+
+@pytest.mark.parametrize("beam,ctc_weight", [(60, 0.3), (40, 0.0), (48, 1.0)])
+def test_beam_up_to_64_vs_oracle(beam, ctc_weight):
+    """Beams beyond one warp of slots (the reference's Librispeech decode_asr.yaml uses beam 60, egs2/librispeech/asr1/conf/decode_asr.yaml:1-3):
+    block-wide beam selection, pre-beam of 1.5 * beam candidates, four cross-attention slot groups; n-best identical to the oracle."""
+    cfg = dict(d_model=128, heads=2, ff=256, enc_layers=2, dec_layers=2, vocab=150, kernel=15)
+    w = random_weights(cfg, seed=13)
+    kw = dict(beam_size=beam, ctc_weight=ctc_weight, maxlenratio=-6.0, nbest=8)
+    s2t = speech2text(cfg, w, **kw)
+    o = oracle.OracleSpeech2Text(cfg, w, **kw)
+    waves = [refbuild.waveform(60 + i, n) for i, n in enumerate([14000, 9000])]
+    res = s2t.batch_decode(waves)
+    for i, wv in enumerate(waves):
+        ref = o(wv)
+        assert len(res[i]) == len(ref)
+        for a, b in zip(res[i], ref):
+            assert a[3].yseq.tolist() == b[3].yseq.tolist()
+            assert abs(a[3].score - b[3].score) <= 2e-4 * max(1.0, abs(b[3].score))
 
 
 def test_global_mvn_bit_exact_vs_reference_fixture(tmp_path):
