@@ -21,7 +21,17 @@ from .ops import _count
 
 
 class Speech2TextStreaming:
-    def __init__(self, asr_model, n_streams: int = 1, device: str = "cuda", ctc_weight: float = 1.0, **unused):
+    def __init__(self, asr_model=None, n_streams: int = 1, device: str = "cuda", ctc_weight: float = 1.0, asr_train_config=None,
+                 asr_model_file=None, **unused):
+        """``asr_model``: a built ESPnetASRModel, or -- as the reference's constructor (asr_inference_streaming.py:46-75) -- ``asr_train_config`` (+
+        ``asr_model_file``) to build it from the reference's own config.yaml / checkpoint."""
+        if asr_model is None or isinstance(asr_model, (str, bytes)) or hasattr(asr_model, "__fspath__"):
+            from .asr_inference import build_model_from_file
+
+            cfg = asr_train_config if asr_model is None else asr_model
+            if cfg is None:
+                raise ValueError("Speech2TextStreaming needs asr_model or asr_train_config")
+            asr_model, _ = build_model_from_file(cfg, asr_model_file, device)
         if ctc_weight != 1.0:
             raise NotImplementedError("espnet_b200.Speech2TextStreaming emits CTC-greedy tokens (ctc_weight=1.0); the block-synchronous beam search "
                                       "of the reference (BatchBeamSearchOnline) is not implemented")
