@@ -296,7 +296,7 @@ def run_streaming(args, rank, local_rank, world):
                                cnn_module_kernel=31, block_size=40, hop_size=16, look_ahead=16))
     torch.manual_seed(0)
     model = espnet_b200.build_model(_ap.Namespace(**y)).to(dev).eval()
-    s2t = espnet_b200.Speech2TextStreaming(model, n_streams=w["streams"], device=str(dev))
+    s2t = espnet_b200.Speech2TextStreaming(model, n_streams=w["streams"], device=str(dev), greedy=True)
     host = waveforms(w["streams"], w["push"] * w["pushes_per_step"], offset=rank * w["streams"]).pin_memory()
 
     def step():

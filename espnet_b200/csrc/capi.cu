@@ -28,7 +28,7 @@ bool pdl_enabled() {
 extern "C" {
 
 const char* espb_last_error(void) { return g_err; }
-int espb_abi_version(void) { return 6; }   // 3: espb_flash_attn_f32; 4: LM fusion helpers; 5: hop / window generality of the frontend entry points; 6: contextual-block (streaming encoder) helpers
+int espb_abi_version(void) { return 7; }   // 7: espb_ctc_extend_state_f32 (streaming beam search); 3: espb_flash_attn_f32; 4: LM fusion helpers; 5: hop / window generality of the frontend entry points; 6: contextual-block (streaming encoder) helpers
 
 int espb_device_sm(int* major, int* minor) {
   int dev = 0;

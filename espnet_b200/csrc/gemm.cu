@@ -575,7 +575,7 @@ gemm_tf32x3_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 //   warp 0: TMA producer (each CTA loads its halves; both signal the leader CTA's full barrier)
 //   warp 1: TMEM alloc (both CTAs) + MMA issue (leader CTA only)
 //   warps 2-9: epilogue; warp e owns TMEM lanes 32*(e%4).. and columns (e/4)*BN/2 ..
-constexpr int V2_THREADS = 320;
+// CTA-pair kernel: warp 0 TMA, warp 1 MMA, EW epilogue warps (64 + 32 * EW threads)
 constexpr int CHUNK_KB = 4;
 
 // rel-pos band (EspbGemmDesc::band_t): a tile of rows [m0, m0+bm) x columns [n0, n0+bn) is needed iff it intersects
@@ -595,18 +595,21 @@ __device__ __forceinline__ float acc_at(const float (&acc)[N], int idx) {
 }
 
 // ACT / SPLIT are compile-time so that the 128-bit epilogue path carries no per-element branches.
-template <int BN, int STAGES, int ACT, bool SPLIT, bool PLAIN>   // PLAIN: no bias / residual / scaling (the attention score and context products)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
+template <int BN, int STAGES, int ACT, bool SPLIT, bool PLAIN, int EW>   // EW: epilogue warps (8 or 16: 16 halves the accumulator registers per thread); PLAIN: no bias / residual / scaling (the attention score and context products)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym, int axm, int aym) {
   constexpr int BH = BN / 2;                      // B rows staged by each CTA
   constexpr int B_TILE_BYTES = BH * 128;
   constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  constexpr int CW = BN / 2;                      // accumulator columns per epilogue warp
-  constexpr int XP_FLOATS = 16 * 36;              // per-warp transpose buffer of the coalescing epilogue (16 rows x 32 cols, padded)
+  constexpr int CW = BN * 4 / EW;                 // accumulator columns per epilogue warp (EW / 4 column groups x 4 TMEM lane quarters)
+  constexpr int XR = 128 / EW;                    // rows of the per-warp transpose buffer: a 32-row block goes through it in 32 / XR passes
+  constexpr int NH = 32 / XR, ITS = XR / 4;
+  constexpr int LDW = (EW == 16) ? 16 : 32;       // columns per tcgen05.ld of the promotion loop (16 warps run at 112 registers)
+  constexpr int XP_FLOATS = XR * 36;              // per-warp transpose buffer of the coalescing epilogue (XR rows x 32 cols, padded)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t xp_base = smem_base + STAGES * STAGE_BYTES;            // 8 warps x [32][33] floats
-  const uint32_t bar_base = xp_base + 8 * XP_FLOATS * 4;
+  const uint32_t bar_base = xp_base + EW * XP_FLOATS * 4;
   const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * STAGES;
   const uint32_t tfull_bar = bar_base + 16 * STAGES, tempty_bar = tfull_bar + 16;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -625,7 +628,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 16); }  // 8 epilogue warps x 2 CTAs
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar + 8 * b, 1); mbar_init(tempty_bar + 8 * b, 2 * EW); }  // EW epilogue warps x 2 CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -728,12 +731,13 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         mbar_wait(tfull_bar + 8 * b, (uint32_t)((cg >> 1) & 1));
         tcgen05_fence_after();
 #pragma unroll
-        for (int j = 0; j < CW / 32; ++j) {
-          float v[32];
+        for (int j = 0; j < CW / LDW; ++j) {
+          float v[LDW];
           __syncwarp();
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + half * CW + j * 32), v);
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + half * CW + j * LDW);
+          if (LDW == 32) tmem_ld32(ta, v); else tmem_ld16(ta, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+          for (int i = 0; i < LDW; ++i) acc[j * LDW + i] += v[i];
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -759,7 +763,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const bool split = SPLIT, has_r = ea.R != nullptr;
       float* const crow0 = ea.C + (long long)(row0 + rsub) * ldc;
       const float* const rrow0 = has_r ? ea.R + (long long)(row0 + rsub) * ldr : nullptr;
-      float* const wrow = xp + (lane & 15) * 36;
+      float* const wrow = xp + (lane & (XR - 1)) * 36;
       const float* const rbase = xp + rsub * 36 + c4;
       // 128-bit path: row / column predicates only (warp-uniform block skips), pointers advanced incrementally
       if (vec_ok) {
@@ -772,17 +776,17 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             // interior block of a product without bias / residual / scaling (attention scores, context): straight-line transpose + stores,
             // no per-row or per-column predicates (the generic path below spends most of its issue slots on them)
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+            for (int hh = 0; hh < NH; ++hh) {
               __syncwarp();
-              if ((lane >> 4) == hh) {
+              if ((lane / XR) == hh) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
                   *reinterpret_cast<float4*>(wrow + i) = make_float4(acc[j * 32 + i], acc[j * 32 + i + 1], acc[j * 32 + i + 2], acc[j * 32 + i + 3]);
               }
               __syncwarp();
-              float* cpi = crow0 + (long long)(hh * 16) * ldc + colb + c4;
+              float* cpi = crow0 + (long long)(hh * XR) * ldc + colb + c4;
 #pragma unroll 2
-              for (int it = 0; it < 4; ++it, cpi += 4 * ldc) {
+              for (int it = 0; it < ITS; ++it, cpi += 4 * ldc) {
                 const float4 v = *reinterpret_cast<const float4*>(rbase + it * 4 * 36);
                 if (SPLIT) {
                   float4 h, l;
@@ -802,25 +806,25 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (!PLAIN && has_b && c_full) b4 = __ldg(reinterpret_cast<const float4*>(ea.bias + col));
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
+          for (int hh = 0; hh < NH; ++hh) {
             __syncwarp();
-            if ((lane >> 4) == hh) {
+            if ((lane / XR) == hh) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4)
                 *reinterpret_cast<float4*>(wrow + i) = make_float4(acc[j * 32 + i], acc[j * 32 + i + 1], acc[j * 32 + i + 2], acc[j * 32 + i + 3]);
             }
             __syncwarp();
-            float* cp = crow0 + (long long)(hh * 16) * ldc + col;
-            float4 rv[4];
+            float* cp = crow0 + (long long)(hh * XR) * ldc + col;
+            float4 rv[ITS];
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
+            for (int it = 0; it < ITS; ++it) {
               rv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (!PLAIN && has_r && c_full && hh * 16 + it * 4 < rows_left)
-                rv[it] = *reinterpret_cast<const float4*>(rrow0 + (long long)(hh * 16 + it * 4) * ldr + col);
+              if (!PLAIN && has_r && c_full && hh * XR + it * 4 < rows_left)
+                rv[it] = *reinterpret_cast<const float4*>(rrow0 + (long long)(hh * XR + it * 4) * ldr + col);
             }
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int rl = hh * 16 + it * 4;
+            for (int it = 0; it < ITS; ++it) {
+              const int rl = hh * XR + it * 4;
               if (rl >= rows_left) continue;
               const float4 v = *reinterpret_cast<const float4*>(rbase + it * 4 * 36);
               float* cpi = cp + (long long)(it * 4) * ldc;
@@ -864,14 +868,14 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           const int colb = n0 + half * CW + j * 32;
           if (row0 >= p.M || colb >= Ncols) continue;
 #pragma unroll 1
-          for (int hh = 0; hh < 2; ++hh) {
+          for (int hh = 0; hh < NH; ++hh) {
             __syncwarp();
-            if ((lane >> 4) == hh) {
+            if ((lane / XR) == hh) {
               for (int i = 0; i < 32; ++i) wrow[i] = acc_at(acc, j * 32 + i);
             }
             __syncwarp();
-            for (int it = 0; it < 4; ++it) {
-              const int rl = hh * 16 + it * 4;
+            for (int it = 0; it < ITS; ++it) {
+              const int rl = hh * XR + it * 4;
               if (rl >= rows_left) continue;
               for (int i = 0; i < 4; ++i) {
                 const int col = colb + c4 + i;
@@ -989,14 +993,14 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc
   return ESPB_OK;
 }
 
-template <int BN, int STAGES, int ACT, bool SPLIT, bool PLAIN>
-int launch_tc2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
-  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * (BN / 2) * 128) + 8 * 16 * 36 * 4 + 1024 + 16 * STAGES + 64;
+template <int BN, int STAGES, int ACT, bool SPLIT, bool PLAIN, int EW>
+int launch_tc2_ew(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
+  constexpr int smem = STAGES * (2 * A_TILE_BYTES + 2 * (BN / 2) * 128) + 128 * 36 * 4 + 1024 + 16 * STAGES + 64;
   static_assert(smem <= 232448, "dynamic shared memory budget exceeded");
   static bool attr_set = false;
   static int num_sms = 0;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tf32x3_2cta_kernel<BN, STAGES, ACT, SPLIT, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tf32x3_2cta_kernel<BN, STAGES, ACT, SPLIT, PLAIN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       espb_set_error("cudaFuncSetAttribute(max dynamic smem) failed");
       return ESPB_ERR_CUDA;
     }
@@ -1008,9 +1012,23 @@ int launch_tc2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmD
   const long long tiles = (long long)((d.M + 255) / 256) * ((d.N + BN - 1) / BN) * d.nbx * d.nby;
   const long long pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;   // persistent: one CTA pair per SM pair
   dim3 grid((unsigned)(2 * pairs), 1, 1);
-  gemm_tf32x3_2cta_kernel<BN, STAGES, ACT, SPLIT, PLAIN><<<grid, V2_THREADS, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
+  gemm_tf32x3_2cta_kernel<BN, STAGES, ACT, SPLIT, PLAIN, EW><<<grid, 64 + 32 * EW, smem, stream>>>(tmA, tmB, d, bxm, bym, axm, aym);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
+}
+
+// 256 accumulator columns with a hi / lo split output: 16 epilogue warps x 64 columns (half the accumulator registers per thread, twice the
+// warps to hide the latency of the activation / split / two-plane store chain).  Measured at M 59968 (scripts/gemm_enc_microbench.py): FFN w_1
+// (Swish, split) 653 -> 588 us, plain split N 512 215 -> 168 us; the single-plane epilogues are store-light and 2-3 % faster with 8 warps, so
+// they keep them.  ESPB_GEMM_EW8=1 forces the 8-warp epilogue everywhere (A/B measurements).
+template <int BN, int STAGES, int ACT, bool SPLIT, bool PLAIN>
+int launch_tc2_v(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemmDesc& d, int bxm, int bym, int axm, int aym, cudaStream_t stream) {
+  if (BN >= 256 && SPLIT) {
+    static int ew8 = -1;
+    if (ew8 < 0) ew8 = getenv("ESPB_GEMM_EW8") ? 1 : 0;
+    if (!ew8) return launch_tc2_ew<BN, STAGES, ACT, SPLIT, PLAIN, (BN >= 256 && SPLIT) ? 16 : 8>(tmA, tmB, d, bxm, bym, axm, aym, stream);
+  }
+  return launch_tc2_ew<BN, STAGES, ACT, SPLIT, PLAIN, 8>(tmA, tmB, d, bxm, bym, axm, aym, stream);
 }
 
 template <int BN, int STAGES>

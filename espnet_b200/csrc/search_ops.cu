@@ -732,6 +732,25 @@ __global__ void ctc_init_state_kernel(const float* __restrict__ logp, int Tmax, 
   s_prev[s] = 0.f;
 }
 
+// Streaming extension of a prefix state to a longer encoder output (CTCPrefixScoreTH.extend_state, ctc_prefix_score.py:251-270; Eq. 14 of
+// arXiv:2006.14941): frames [0, T_old) are kept; for the new frames the prefix can only be continued by blanks:
+// r^n[t] = logzero, r^b[t] = r^b[t-1] + x[t][blank].  One thread per state, sequential over the (few) new frames like the reference's loop.
+__global__ void ctc_extend_state_kernel(const float* __restrict__ logp, int T_new, int V, int blank, int n, const float* __restrict__ r_old, int T_old,
+                                        float* __restrict__ r_new) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const float4* ro = reinterpret_cast<const float4*>(r_old) + (long long)s * T_old;
+  float4* rn = reinterpret_cast<float4*>(r_new) + (long long)s * T_new;
+  const int keep = min(T_old, T_new);
+  for (int t = 0; t < keep; ++t) rn[t] = ro[t];
+  float rb = keep > 0 ? ro[keep - 1].y : LOGZERO;
+  for (int t = max(keep, 1); t < T_new; ++t) {
+    rb += logp[(long long)t * V + blank];
+    rn[t] = make_float4(LOGZERO, rb, logaddexp(LOGZERO, rb), 0.f);
+  }
+  if (keep == 0 && T_new > 0) rn[0] = make_float4(LOGZERO, LOGZERO, logaddexp(LOGZERO, LOGZERO), 0.f);
+}
+
 // log_phi[t] of the previous state: r_sum unless the candidate repeats the last label (ctc_prefix_score.py:135-144).
 // State layout: float4 per frame (r^n, r^b, r_sum = logaddexp(r^n, r^b), 0) so that scoring needs no transcendental for log_phi.
 __device__ __forceinline__ float ctc_phi(const float4* __restrict__ rp, int t, bool same) {
@@ -1211,6 +1230,14 @@ int espb_ctc_init_state_f32(const float* logp, int U, int Tmax, int V, const int
                             cudaStream_t stream) {
   const int n = U * W;
   ctc_init_state_kernel<<<(n + 63) / 64, 64, 0, stream>>>(logp, Tmax, V, lens, blank, W, n, r, s_prev);
+  ESPB_CHECK_LAUNCH();
+  return ESPB_OK;
+}
+
+int espb_ctc_extend_state_f32(const float* logp, int T_new, int V, int blank, int n, const float* r_old, int T_old, float* r_new, cudaStream_t stream) {
+  if (n <= 0) return ESPB_OK;
+  if (T_old < 1 || T_new < T_old) { espb_set_error("ctc_extend_state: need 1 <= T_old <= T_new"); return ESPB_ERR_ARG; }
+  ctc_extend_state_kernel<<<(n + 63) / 64, 64, 0, stream>>>(logp, T_new, V, blank, n, r_old, T_old, r_new);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

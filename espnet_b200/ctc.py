@@ -124,6 +124,33 @@ class CTCPrefixScorer:
     def final_score(self, state) -> float:
         return 0.0
 
+    # -- streaming extension (scorers/ctc.py:128-157 over ctc_prefix_score.py:226-270; Eq. 14 of arXiv:2006.14941)
+    @torch.no_grad()
+    def extend_prob(self, x: torch.Tensor):
+        """x (T_new, D): the encoder output so far, grown by a block.  The posteriors are per frame, so recomputing all of them equals the
+        reference's 'keep the old rows, append the new ones'."""
+        if self.logp is None or x.shape[0] > self.T:
+            self.batch_init_state(x)
+
+    @torch.no_grad()
+    def extend_state(self, state):
+        """List of per-hypothesis states (None before the first step) -> states over the extended posteriors."""
+        todo = [i for i, st in enumerate(state) if st is not None and st.r.shape[0] < self.T]
+        if not todo:
+            return list(state)
+        out = list(state)
+        by_len = {}
+        for i in todo:
+            by_len.setdefault(state[i].r.shape[0], []).append(i)
+        for t_old, idx in by_len.items():
+            r_old = torch.stack([state[i].r for i in idx]).contiguous()
+            r_new = torch.empty(len(idx), self.T, 4, dtype=torch.float32, device=r_old.device)
+            call("espb_ctc_extend_state_f32", ptr(self.logp), self.T, self.V, self.blank, len(idx), ptr(r_old), t_old, ptr(r_new))
+            _count()
+            for j, i in enumerate(idx):
+                out[i] = _CTCHypState(r_new[j], state[i].s)
+        return out
+
     @torch.no_grad()
     def batch_score_partial(self, y: torch.Tensor, ids: torch.Tensor, state, x: torch.Tensor):
         """y (n, len) int64 prefixes, ids (n, k) int64 tokens to score, state: list of n hypothesis states (None before the first step)."""

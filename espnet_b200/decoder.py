@@ -139,13 +139,15 @@ class TransformerDecoder(torch.nn.Module):
 
     def _iface_memory(self, x, n, need_len):
         """Cross-attention K / V of the utterance whose encoder output is x (T, D): projected once and kept while x is the same tensor."""
-        key = (x.data_ptr(), tuple(x.shape), x._version)
+        key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x._version)
         c = getattr(self, "_iface", None)
         if c is None or c["key"] != key:
             T = x.shape[0]
             self.ws_tag = "iface"
-            c = self._iface = dict(key=key, enc_split=split_from(x.contiguous().float()), lens32=torch.tensor([T], dtype=torch.int32, device=x.device),
-                                   T=T, st=None)
+            # ``x_ref`` keeps the storage alive: while it is cached no other encoder output can be allocated at the same address, so an equal key
+            # means the same data (a freed tensor's address is readily reused for the next utterance of the same length)
+            c = self._iface = dict(key=key, x_ref=x, enc_split=split_from(x.contiguous().float()),
+                                   lens32=torch.tensor([T], dtype=torch.int32, device=x.device), T=T, st=None)
         st = c["st"]
         if st is None or st["n"] != n or st["max_len"] < need_len:
             cap = max(32, 1 << (need_len - 1).bit_length())

@@ -62,6 +62,7 @@ _SIGS = {
     "espb_dec_src_attn_f32": [P, P, P, I, I, P, I, I, I, P, L, P],
     "espb_rows_topk_f32": [P, L, L, I, F, I, P, P, P],
     "espb_ctc_init_state_f32": [P, I, I, I, P, I, I, P, P, P],
+    "espb_ctc_extend_state_f32": [P, I, I, I, I, P, I, P, P],
     "espb_ctc_score_cands_f32": [P, I, I, I, P, I, I, I, P, P, P, I, P, P, I, P, P, P, I, P],
     "espb_ctc_score_dense_f32": [P, I, I, I, P, I, I, I, P, P, P, I, P, P],
     "espb_beam_select": [P] * 18 + [I] + [P, P, P] + [I, I, I, I, I, P, P, P, I, F, F, F, I, P, P, P, P, P, I, I, P],
@@ -76,7 +77,7 @@ _SIGS = {
     "espb_count_active_i32": [P, I, P, P],
 }
 
-ABI_VERSION = 6   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
+ABI_VERSION = 7   # espb_abi_version() of the library this binding matches (include/espnet_b200.h)
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + ["espb_last_error", "espb_abi_version", "espb_device_sm", "espb_frontend_blocks"])
 
 

@@ -143,6 +143,9 @@ int espb_rows_topk_f32(const float* x, long long rows, long long ld, int V, floa
  * r [n][Tmax][4] forward variables per frame (r^n, r^b, r_sum = logaddexp(r^n, r^b), pad), s_prev [n] previous log_psi. */
 int espb_ctc_init_state_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int W, float* r, float* s_prev,
                             cudaStream_t stream);
+/* CTCPrefixScoreTH.extend_state (ctc_prefix_score.py:251-270): n states [T_old][4] -> [T_new][4] over the extended posteriors logp [T_new][V]
+ * of one stream (new frames continue the prefix by blanks only). */
+int espb_ctc_extend_state_f32(const float* logp, int T_new, int V, int blank, int n, const float* r_old, int T_old, float* r_new, cudaStream_t stream);
 int espb_ctc_score_cands_f32(const float* logp, int U, int Tmax, int V, const int* lens, int blank, int eos, int W, const float* r_prev,
                              const float* s_prev, const int* last_tok, int out_len, const int* step_ptr, const int* cand, int P, float* part,
                              float* psi, int* valid, int token_major, cudaStream_t stream);

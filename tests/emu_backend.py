@@ -360,6 +360,16 @@ def _ctc_init_state(logp, U, Tmax, V, lens, blank, W, r, s_prev):
         s_prev.view(-1)[s] = 0.0
 
 
+def _ctc_extend_state(logp, T_new, V, blank, n, r_old, T_old, r_new):
+    ro, rn, lp = r_old.reshape(-1)[: n * T_old * 4].view(n, T_old, 4), r_new.view(-1)[: n * T_new * 4].view(n, T_new, 4), logp.view(-1)[: T_new * V].view(T_new, V)
+    for s in range(n):
+        rn[s, :T_old] = ro[s]
+        rb = ro[s, T_old - 1, 1].clone()
+        for t in range(max(T_old, 1), T_new):
+            rb = rb + lp[t, blank]
+            rn[s, t] = torch.tensor([LOGZERO, float(rb), _lae(LOGZERO, float(rb)), 0.0])
+
+
 def _transpose_tv(x, U, Tmax, V, xt):
     xt.view(U, V, Tmax).copy_(x.view(U, Tmax, V).transpose(1, 2))
 
@@ -513,7 +523,7 @@ def _count_active(active, n, out):
 
 _TABLE.update({"espb_log_softmax_rows_f32": _log_softmax_rows, "espb_argmax_rows_f32": _argmax_rows, "espb_ctc_collapse_i32": _ctc_collapse,
                "espb_rows_topk_f32": _rows_topk, "espb_dec_embed_f32": _dec_embed, "espb_dec_self_attn_f32": _dec_self_attn,
-               "espb_dec_src_attn_f32": _dec_src_attn, "espb_ctc_init_state_f32": _ctc_init_state, "espb_transpose_tv_f32": _transpose_tv,
+               "espb_dec_src_attn_f32": _dec_src_attn, "espb_ctc_init_state_f32": _ctc_init_state, "espb_ctc_extend_state_f32": _ctc_extend_state, "espb_transpose_tv_f32": _transpose_tv,
                "espb_ctc_score_cands_f32": _ctc_score_cands, "espb_ctc_score_dense_f32": _ctc_score_dense, "espb_ctc_advance_f32": _ctc_advance,
                "espb_beam_select": _beam_select, "espb_anc_update_i32": _anc_update, "espb_step_inc_i32": _step_inc,
                "espb_count_active_i32": _count_active})

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     handle.espb_abi_version.restype = ctypes.c_int
     from espnet_b200 import lib as _l
 
-    assert handle.espb_abi_version() == _l.ABI_VERSION == 6
+    assert handle.espb_abi_version() == _l.ABI_VERSION == 7
 
 
 def test_binding_arity_matches_header():

@@ -88,8 +88,8 @@ def test_search_rejects_unsupported_setups():
 
     dec = espnet_b200.TransformerDecoder(50, 64, attention_heads=4, linear_units=128, num_blocks=1)
     ctc = espnet_b200.CTC(50, 64)
-    with pytest.raises(NotImplementedError):       # beam wider than one warp's selection capacity
-        BatchBeamSearch(dict(decoder=dec, ctc=ctc), dict(decoder=0.7, ctc=0.3), 33, 50, 49, 49, pre_beam_score_key="full")
+    with pytest.raises(NotImplementedError):       # beam wider than the selection kernel's capacity (64)
+        BatchBeamSearch(dict(decoder=dec, ctc=ctc), dict(decoder=0.7, ctc=0.3), 65, 50, 49, 49, pre_beam_score_key="full")
     with pytest.raises(NotImplementedError):       # joint decoding needs vocab > 1.5 * beam (pre-beam)
         BatchBeamSearch(dict(decoder=dec, ctc=ctc), dict(decoder=0.7, ctc=0.3), 40, 50, 49, 49, pre_beam_score_key="full")
     with pytest.raises(ValueError):                # all scorer weights zero

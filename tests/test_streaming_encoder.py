@@ -71,7 +71,7 @@ def _frontend_model(device, n_streams):
     model = types.SimpleNamespace(frontend=fe, normalize=None, blank_id=0, encoder=None, ctc=None)
     model.to = lambda d: model
     model.eval = lambda: model
-    return espnet_b200.Speech2TextStreaming(model, n_streams=n_streams, device=device)
+    return espnet_b200.Speech2TextStreaming(model, n_streams=n_streams, device=device, greedy=True)
 
 
 def _run_frontend(s2t, z, device, n_streams):
@@ -122,7 +122,7 @@ def test_streaming_speech2text_ctc_greedy_equals_whole_utterance_collapse():
     torch.manual_seed(3)
     model = espnet_b200.build_model(argparse.Namespace(**y)).cuda().eval()
     n_streams, wave = 4, refbuild.waveform(5, 48000)
-    s2t = espnet_b200.Speech2TextStreaming(model, n_streams=n_streams, device="cuda")
+    s2t = espnet_b200.Speech2TextStreaming(model, n_streams=n_streams, device="cuda", greedy=True)
     frames = []
     orig = model.encoder.forward
 

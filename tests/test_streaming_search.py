@@ -1,0 +1,73 @@
+"""Streaming row: espnet_b200.Speech2TextStreaming with the block-synchronous beam search (search_online.BatchBeamSearchOnline over
+TransformerDecoder.batch_score + CTCPrefixScorer.batch_score_partial / extend_prob / extend_state + LengthBonus) against the n-best the UNMODIFIED
+reference Speech2TextStreaming returned for EVERY push of a waveform (tests/golden/streaming_search.npz, made by
+tests/golden/make_golden_streaming_search.py): joint CTC/attention, joint with length bonus and repetition detection off, CTC only, attention-heavy
+with a maxlenratio.  CPU: host logic with the kernels emulated; -m gpu: the CUDA kernels.
+Tolerance: identical token sequences; total and per-scorer scores rtol 2e-4 + atol 2e-3 (scores are O(10..100) sums of log-probabilities)."""
+import argparse
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "streaming_search.npz")
+
+
+def _model(z, device):
+    import espnet_b200
+
+    y = json.loads(str(z["yaml"]))
+    model = espnet_b200.build_model(argparse.Namespace(**y))
+    model.load_state_dict({k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}, strict=True)
+    return model.to(device).eval(), argparse.Namespace(**y)
+
+
+def _run(device, names=None, n_streams=1):
+    import espnet_b200
+
+    z = np.load(GOLD)
+    model, _ = _model(z, device)
+    settings = json.loads(str(z["settings"]))
+    wave, pushes = torch.from_numpy(z["wave"]), z["pushes"].tolist()
+    for name, kw in settings.items():
+        if names is not None and name not in names:
+            continue
+        s2t = espnet_b200.Speech2TextStreaming(model, n_streams=n_streams, device=device, **kw)
+        pos = 0
+        for i, n in enumerate(pushes):
+            chunk = wave[pos:pos + n]
+            res = s2t(chunk if n_streams == 1 else chunk[None].repeat(n_streams, 1), is_final=(i == len(pushes) - 1))
+            pos += n
+            for per_stream in ([res] if n_streams == 1 else res):
+                assert len(per_stream) == int(z[f"{name}:{i}:n"]), (name, i, len(per_stream))
+                for j, (_, _, token_int, hyp) in enumerate(per_stream):
+                    key = f"{name}:{i}:{j}"
+                    assert hyp.yseq.tolist() == z[key + ":yseq"].tolist(), (key, hyp.yseq.tolist(), z[key + ":yseq"].tolist())
+                    assert token_int == z[key + ":token_int"].tolist(), key
+                    ref = float(z[key + ":score"])
+                    assert abs(float(hyp.score) - ref) <= 2e-4 * abs(ref) + 2e-3, (key, float(hyp.score), ref)
+                    for k, v in hyp.scores.items():
+                        r = float(z[f"{key}:score:{k}"])
+                        assert abs(float(v) - r) <= 2e-4 * abs(r) + 2e-3, (key, k, float(v), r)
+
+
+@pytest.mark.parametrize("name", ["joint", "joint_pen_norep", "ctc_only", "att_heavy_maxlen"])
+def test_streaming_beam_search_host_logic_vs_reference_fixture(monkeypatch, name):
+    import emu_backend
+
+    emu_backend.install_search(monkeypatch)
+    emu_backend.install_frontend(monkeypatch)
+    _run("cpu", [name])
+    assert "espb_ctc_extend_state_f32" in emu_backend.calls
+
+
+@pytest.mark.gpu
+def test_streaming_beam_search_cuda_vs_reference_fixture():
+    _run("cuda")
+
+
+@pytest.mark.gpu
+def test_streaming_beam_search_cuda_three_streams_in_lock_step():
+    _run("cuda", ["joint"], n_streams=3)
