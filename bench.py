@@ -437,11 +437,26 @@ def run_b200(args, rank, local_rank, world):
             if en > st:
                 busy += en - st
                 cur_end = en
+        # exclusive time per kernel name: the part of each interval during which no other kernel runs (what the kernel adds to the critical
+        # path when branches of the step graph overlap, e.g. the CTC state recursion under the decoder pass)
+        pts = sorted([(e.time_range.start, 1, i) for i, e in enumerate(evs)] + [(e.time_range.end, 0, i) for i, e in enumerate(evs)])
+        excl = collections.defaultdict(float)
+        live, last_t = set(), pts[0][0]
+        for t, kind, i in pts:
+            if len(live) == 1 and t > last_t:
+                excl[next(iter(live))] += t - last_t
+            last_t = t
+            (live.add if kind == 1 else live.discard)(i)
+        excl_by_name = collections.defaultdict(float)
+        for i, v in excl.items():
+            nm = _re.sub(r"\(.*", "", _re.sub(r"^void |\(anonymous namespace\)::|<unnamed>::", "", evs[i].name))
+            excl_by_name[nm] += v
         tot = sum(v[1] for v in agg.values())
         print(f"[trace] {args.workload}: {len(evs)} device activities, span {(t_last - t_first) / 1e3:.2f} ms, device busy (union) {busy / 1e3:.2f} ms, "
               f"sum of durations {tot / 1e3:.2f} ms", file=sys.stderr)
         for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:50]:
-            print(f"[trace] {100 * us / tot:6.2f}%  {us / 1e3:9.3f} ms  {c:5d}x  avg {us / c:9.1f} us  {k[:120]}", file=sys.stderr)
+            print(f"[trace] {100 * us / tot:6.2f}%  {us / 1e3:9.3f} ms  {c:5d}x  avg {us / c:9.1f} us  exclusive {excl_by_name.get(k, 0.0) / 1e3:8.3f} ms  {k[:120]}",
+                  file=sys.stderr)
         return
     if args.profile_one_step:   # for ncu --profile-from-start off: exactly one resident step inside the profiler range
         torch.cuda.synchronize()

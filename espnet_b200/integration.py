@@ -12,7 +12,8 @@ import espnet_b200
 
 NAMES = {"frontend": {"b200_default": "DefaultFrontend"},
          "normalize": {"b200_utterance_mvn": "UtteranceMVN", "b200_global_mvn": "GlobalMVN"},
-         "encoder": {"b200_conformer": "ConformerEncoder", "b200_transformer": "TransformerEncoder"},
+         "encoder": {"b200_conformer": "ConformerEncoder", "b200_transformer": "TransformerEncoder",
+                     "b200_contextual_block_conformer": "ContextualBlockConformerEncoder"},
          "decoder": {"b200_transformer": "TransformerDecoder"}}
 
 
