@@ -451,6 +451,13 @@ def run_b200(args, rank, local_rank, world):
         for i, v in excl.items():
             nm = _re.sub(r"\(.*", "", _re.sub(r"^void |\(anonymous namespace\)::|<unnamed>::", "", evs[i].name))
             excl_by_name[nm] += v
+        if os.environ.get("ESPB_TRACE_DUMP"):   # timeline around the k-th CTC state recursion: which kernels overlap it
+            adv = [i for i, e in enumerate(evs) if "ctc_advance" in e.name]
+            if len(adv) > 10:
+                i0 = adv[10]
+                t0 = evs[i0].time_range.start
+                for e in evs[max(0, i0 - 3): i0 + int(os.environ["ESPB_TRACE_DUMP"])]:
+                    print(f"[timeline] {e.time_range.start - t0:9.1f} .. {e.time_range.end - t0:9.1f} us  {_re.sub(r"[(].*", "", _re.sub(r"^void |[(]anonymous namespace[)]::|<unnamed>::", "", e.name))[:60]}", file=sys.stderr)
         tot = sum(v[1] for v in agg.values())
         print(f"[trace] {args.workload}: {len(evs)} device activities, span {(t_last - t_first) / 1e3:.2f} ms, device busy (union) {busy / 1e3:.2f} ms, "
               f"sum of durations {tot / 1e3:.2f} ms", file=sys.stderr)
