@@ -11,35 +11,38 @@ from typing import Iterable, List, Optional, Union
 import numpy as np
 
 
+def _read_token_file(path) -> List[str]:
+    """One token per line; only the line terminator / trailing blanks are stripped, so a token that IS a leading space symbol survives."""
+    return [ln[:1] + ln[1:].rstrip() for ln in Path(path).read_text(encoding="utf-8").splitlines(keepends=True)]
+
+
 class TokenIDConverter:
+    """id <-> token table with the reference's interface (token_list, token2id, unk_id, ids2tokens, tokens2ids, get_num_vocabulary_size) and
+    its error conditions (duplicated symbol, missing unknown symbol: RuntimeError; non-1-D id array: ValueError)."""
+
     def __init__(self, token_list: Union[Path, str, Iterable[str]], unk_symbol: str = "<unk>"):
-        if isinstance(token_list, (Path, str)):
-            self.token_list: List[str] = []
-            with Path(token_list).open("r", encoding="utf-8") as f:
-                for line in f:
-                    self.token_list.append(line[0] + line[1:].rstrip())   # keep a leading space symbol
-        else:
-            self.token_list = list(token_list)
-        self.token2id = {}
-        for i, t in enumerate(self.token_list):
-            if t in self.token2id:
-                raise RuntimeError(f'Symbol "{t}" is duplicated')
-            self.token2id[t] = i
-        self.unk_symbol = unk_symbol
+        self.token_list: List[str] = _read_token_file(token_list) if isinstance(token_list, (Path, str)) else list(token_list)
+        self.token2id = {t: i for i, t in enumerate(self.token_list)}
+        if len(self.token2id) != len(self.token_list):
+            seen = set()
+            dup = next(t for t in self.token_list if t in seen or seen.add(t))
+            raise RuntimeError(f'Symbol "{dup}" is duplicated')
         if unk_symbol not in self.token2id:
             raise RuntimeError(f"Unknown symbol '{unk_symbol}' doesn't exist in the token_list")
-        self.unk_id = self.token2id[unk_symbol]
+        self.unk_symbol, self.unk_id = unk_symbol, self.token2id[unk_symbol]
 
     def get_num_vocabulary_size(self) -> int:
         return len(self.token_list)
 
     def ids2tokens(self, integers: Union[np.ndarray, Iterable[int]]) -> List[str]:
-        if isinstance(integers, np.ndarray) and integers.ndim != 1:
+        if getattr(integers, "ndim", 1) != 1:
             raise ValueError(f"Must be 1 dim ndarray, but got {integers.ndim}")
-        return [self.token_list[i] for i in integers]
+        table = self.token_list
+        return [table[int(i)] for i in integers]
 
     def tokens2ids(self, tokens: Iterable[str]) -> List[int]:
-        return [self.token2id.get(i, self.unk_id) for i in tokens]
+        lookup, unk = self.token2id.get, self.unk_id
+        return [lookup(t, unk) for t in tokens]
 
 
 class CharTokenizer:
