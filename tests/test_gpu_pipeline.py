@@ -292,6 +292,39 @@ def test_wide_beam_vs_oracle(heads, beam, ctc_weight):
             assert abs(a[3].score - b[3].score) <= 2e-4 * max(1.0, abs(b[3].score))
 
 
+def test_long_utterance_90s_ragged_batch_vs_oracle():
+    """Maximum-size edge: a 90-s utterance (T = 2812 encoder frames: several key tiles beyond anything else in the suite, a 5623-column rel-pos
+    band, the cross-attention and CTC recursions over 2812 frames) batched with a 2-s one; encoder output per utterance (atol 1e-4) and the joint
+    beam-4 n-best of the first 5 steps vs the oracle."""
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    cfg = dict(d_model=128, heads=2, ff=256, enc_layers=2, dec_layers=1, vocab=60, kernel=15)
+    w = random_weights(cfg, seed=21)
+    kw = dict(beam_size=4, ctc_weight=0.3, maxlenratio=-5.0, nbest=2)
+    s2t = speech2text(cfg, w, **kw)
+    o = oracle.OracleSpeech2Text(cfg, w, **kw)
+    waves = [refbuild.waveform(300, 90 * 16000), refbuild.waveform(301, 2 * 16000)]
+    speech = torch.zeros(2, 90 * 16000)
+    for i, wv in enumerate(waves):
+        speech[i, : wv.numel()] = wv
+    lens = torch.tensor([wv.numel() for wv in waves])
+    enc, olens = s2t.asr_model.encode(speech.cuda(), lens.cuda())
+    assert olens.tolist() == [2812, 62]
+    for i, wv in enumerate(waves):
+        ref_enc = o.encode(wv)
+        got = enc[i, : int(olens[i])].cpu()
+        assert got.shape == ref_enc.shape
+        err = float((got - ref_enc).abs().max())
+        print(f"utt {i}: T {int(olens[i])}, encoder max abs err {err:.2e}")
+        assert err < 1e-4
+    res = s2t.batch_decode(waves)
+    for i, wv in enumerate(waves):
+        ref = o(wv)
+        assert len(res[i]) == len(ref)
+        for a, b in zip(res[i], ref):
+            assert a[3].yseq.tolist() == b[3].yseq.tolist()
+            assert abs(a[3].score - b[3].score) <= 2e-4 * max(1.0, abs(b[3].score))
+
+
 def test_beam_wider_than_64_is_refused():
     z, cfg, w = load("tiny")
     with pytest.raises(NotImplementedError):

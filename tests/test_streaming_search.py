@@ -63,6 +63,34 @@ def test_streaming_beam_search_host_logic_vs_reference_fixture(monkeypatch, name
     assert "espb_ctc_extend_state_f32" in emu_backend.calls
 
 
+def test_streaming_speech2text_from_config_and_checkpoint_files(monkeypatch, tmp_path):
+    """The reference's constructor form (asr_inference_streaming.py:46-75): asr_train_config + asr_model_file; block sizes come from encoder_conf."""
+    import yaml
+
+    import emu_backend
+    import espnet_b200
+
+    emu_backend.install_search(monkeypatch)
+    emu_backend.install_frontend(monkeypatch)
+    z = np.load(GOLD)
+    cfg_path, pth = tmp_path / "config.yaml", tmp_path / "model.pth"
+    cfg_path.write_text(yaml.safe_dump(json.loads(str(z["yaml"]))))
+    torch.save({k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}, pth)
+    kw = json.loads(str(z["settings"]))["joint"]
+    s2t = espnet_b200.Speech2TextStreaming(asr_train_config=str(cfg_path), asr_model_file=str(pth), device="cpu", **kw)
+    assert (s2t.searches[0].block_size, s2t.searches[0].hop_size, s2t.searches[0].look_ahead) == (40, 16, 16)
+    wave, pushes = torch.from_numpy(z["wave"]), z["pushes"].tolist()
+    pos = 0
+    for i, n in enumerate(pushes):
+        res = s2t(wave[pos:pos + n].numpy(), is_final=(i == len(pushes) - 1))      # numpy input like the reference accepts
+        pos += n
+        assert len(res) == int(z[f"joint:{i}:n"])
+        for j, r in enumerate(res):
+            assert r[2] == z[f"joint:{i}:{j}:token_int"].tolist() and r[1] == [f"t{t - 2}" for t in r[2]]
+    with pytest.raises(NotImplementedError):
+        espnet_b200.BatchBeamSearchOnline({}, {}, 2, 10, 9, 9, time_sync=True)
+
+
 @pytest.mark.gpu
 def test_streaming_beam_search_cuda_vs_reference_fixture():
     _run("cuda")
