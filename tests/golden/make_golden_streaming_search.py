@@ -36,20 +36,32 @@ cfg_path = os.path.join(tmp, "config.yaml")
 with open(cfg_path, "w") as f:
     yaml.safe_dump(y, f)
 
+LM = dict(embed_unit=32, att_unit=64, head=4, unit=96, layer=2)
+lm_path = os.path.join(tmp, "lm.yaml")
+with open(lm_path, "w") as f:
+    yaml.safe_dump(dict(token_list=refbuild.token_list(CFG["vocab"]), lm="transformer",
+                        lm_conf=dict(pos_enc="sinusoidal", dropout_rate=0.1, positional_dropout_rate=0.1, attention_dropout_rate=0.1, **LM),
+                        model_conf={}, init=None, use_preprocessor=False), f)
+
 SETTINGS = {
     "joint": dict(beam_size=3, ctc_weight=0.3),
     "joint_pen_norep": dict(beam_size=4, ctc_weight=0.5, penalty=0.4, disable_repetition_detection=True, nbest=3),
     "ctc_only": dict(beam_size=3, ctc_weight=1.0, nbest=2),
     "att_heavy_maxlen": dict(beam_size=2, ctc_weight=0.1, maxlenratio=0.2, nbest=2),
+    "joint_lm": dict(beam_size=3, ctc_weight=0.3, lm_weight=0.5, nbest=2),       # + TransformerLM shallow fusion (lm_train_config)
 }
 wave = refbuild.waveform(7, 52000)
 pushes = [8000, 640, 640, 9000, 12000, 3000, 18720]
 assert sum(pushes) == wave.numel()
-out = {"yaml": np.array(json.dumps(y)), "wave": wave.numpy(), "pushes": np.array(pushes), "settings": np.array(json.dumps(SETTINGS))}
+out = {"lm_conf": np.array(json.dumps(dict(pos_enc="sinusoidal", **LM))), "yaml": np.array(json.dumps(y)), "wave": wave.numpy(), "pushes": np.array(pushes), "settings": np.array(json.dumps(SETTINGS))}
 weights = None
 for name, kw in SETTINGS.items():
     torch.manual_seed(0)
-    s2t = Speech2TextStreaming(asr_train_config=cfg_path, asr_model_file=None, device="cpu", **kw)
+    extra = dict(lm_train_config=lm_path, lm_file=None) if "lm_weight" in kw else {}
+    s2t = Speech2TextStreaming(asr_train_config=cfg_path, asr_model_file=None, device="cpu", **kw, **extra)
+    if extra:
+        for k, v in s2t.beam_search.full_scorers["lm"].state_dict().items():
+            out["lm:" + k] = v.numpy()
     with torch.no_grad():
         for m in s2t.asr_model.modules():
             if isinstance(m, torch.nn.BatchNorm1d):

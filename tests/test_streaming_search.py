@@ -2,7 +2,7 @@
 TransformerDecoder.batch_score + CTCPrefixScorer.batch_score_partial / extend_prob / extend_state + LengthBonus) against the n-best the UNMODIFIED
 reference Speech2TextStreaming returned for EVERY push of a waveform (tests/golden/streaming_search.npz, made by
 tests/golden/make_golden_streaming_search.py): joint CTC/attention, joint with length bonus and repetition detection off, CTC only, attention-heavy
-with a maxlenratio.  CPU: host logic with the kernels emulated; -m gpu: the CUDA kernels.
+with a maxlenratio, joint + TransformerLM shallow fusion.  CPU: host logic with the kernels emulated; -m gpu: the CUDA kernels.
 Tolerance: identical token sequences; total and per-scorer scores rtol 2e-4 + atol 2e-3 (scores are O(10..100) sums of log-probabilities)."""
 import argparse
 import json
@@ -34,7 +34,12 @@ def _run(device, names=None, n_streams=1):
     for name, kw in settings.items():
         if names is not None and name not in names:
             continue
-        s2t = espnet_b200.Speech2TextStreaming(model, n_streams=n_streams, device=device, **kw)
+        extra = {}
+        if "lm_weight" in kw:      # TransformerLM shallow fusion: the fixture carries the reference LM's weights (lm:*) and its lm_conf
+            lm = espnet_b200.TransformerLM(len(json.loads(str(z["yaml"]))["token_list"]), **json.loads(str(z["lm_conf"])))
+            lm.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("lm:")}, strict=True)
+            extra["lm"] = lm.to(device).eval()
+        s2t = espnet_b200.Speech2TextStreaming(model, n_streams=n_streams, device=device, **kw, **extra)
         pos = 0
         for i, n in enumerate(pushes):
             chunk = wave[pos:pos + n]
@@ -53,7 +58,7 @@ def _run(device, names=None, n_streams=1):
                         assert abs(float(v) - r) <= 2e-4 * abs(r) + 2e-3, (key, k, float(v), r)
 
 
-@pytest.mark.parametrize("name", ["joint", "joint_pen_norep", "ctc_only", "att_heavy_maxlen"])
+@pytest.mark.parametrize("name", ["joint", "joint_pen_norep", "ctc_only", "att_heavy_maxlen", "joint_lm"])
 def test_streaming_beam_search_host_logic_vs_reference_fixture(monkeypatch, name):
     import emu_backend
 
