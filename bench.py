@@ -35,6 +35,10 @@ WORKLOADS = {
     "transformer_24l1024_att_64x30s": (dict(d_model=1024, heads=16, ff=4096, enc_layers=24, dec_layers=6, vocab=5000, encoder="transformer"),
                                        30, 64, 5, 0.0, -64.0),
 }
+# The one decoding setup the reference publishes an RTF for (egs2/librispeech/asr1/conf/decode_asr.yaml:1-3, beam 60 / ctc 0.3 /
+# lm 0.6 with a Transformer LM): the same Conformer-large + the Librispeech LM shape (16L / 512d / 8h / 2048 units, embed 128), 16 utterances per GPU.
+WORKLOADS["conformer_large_lm_beam60_16x30s"] = (WORKLOADS["conformer_large_joint_64x30s"][0], 30, 16, 60, 0.3, -64.0)
+LM_FUSION = {"conformer_large_lm_beam60_16x30s": dict(weight=0.6, conf=dict(pos_enc="sinusoidal", embed_unit=128, att_unit=512, head=8, unit=2048, layer=16))}
 METRIC = "utterances/sec (RTF) Conformer-large ASR inference at 1/2/4/8 B200 vs CPU ref"
 # BASELINE.json configs[3] (next row 8f-2): contextual-block Conformer (12L/512d/8h, block 40 / hop 16 / look-ahead 16), 128 live streams per GPU,
 # 40-ms pushes (640 samples).  One "step" = 64 pushes (2.56 s of audio per stream); value = audio seconds processed per second (all streams).
@@ -62,6 +66,20 @@ def model_weights(cfg):
     return _WEIGHTS[key]
 
 
+def lm_weights(workload, vocab):
+    """Random-init (seed 1) TransformerLM weights with the reference's parameter names (espnet2/lm/transformer_lm.py), or None."""
+    spec = LM_FUSION.get(workload)
+    if spec is None:
+        return None
+    key = ("lm", workload)
+    if key not in _WEIGHTS:
+        import espnet_b200
+
+        torch.manual_seed(1)
+        _WEIGHTS[key] = {k: v.detach().clone() for k, v in espnet_b200.TransformerLM(vocab, **spec["conf"]).state_dict().items()}
+    return _WEIGHTS[key]
+
+
 # ----------------------------------------------------------------------------------------------- reference CPU path
 # The reference's own espnet2.bin.asr_inference.Speech2Text (unmodified files under oracle/_ref, made by oracle/install_ref.py where
 # /root/reference is mounted; it travels to the GPU box with the snapshot), batch-1 as the reference decodes, FULL search (all
@@ -84,7 +102,7 @@ def ref_kind():
     return "reference" if install_ref.available() else "port"
 
 
-def _ref_worker(rank, cfg, wfile, beam, ctcw, mlr, inq, outq):
+def _ref_worker(rank, cfg, wfile, beam, ctcw, mlr, inq, outq, lm_spec=None):
     """One decoding process: builds the CPU Speech2Text once, then decodes the waveforms it is sent."""
     import torch as _t
 
@@ -100,13 +118,28 @@ def _ref_worker(rank, cfg, wfile, beam, ctcw, mlr, inq, outq):
         import refbuild
 
         logging.disable(logging.WARNING)
-        s2t = refbuild.build_reference(cfg, seed=0, beam_size=beam, ctc_weight=ctcw, maxlenratio=mlr, nbest=1)
-        s2t.asr_model.load_state_dict(weights, strict=True)       # same weights as the CUDA arm (parity check of the bench)
+        kw = {}
+        if lm_spec is not None:      # LM shallow fusion exactly as a user passes it: lm_train_config (asr_inference.py:178-191)
+            import tempfile
+
+            import yaml
+
+            lm_yaml = os.path.join(tempfile.mkdtemp(prefix="espb_ref_lm_"), "lm.yaml")
+            with open(lm_yaml, "w") as f:
+                yaml.safe_dump(dict(token_list=refbuild.token_list(cfg["vocab"]), lm="transformer", model_conf={}, init=None, use_preprocessor=False,
+                                    lm_conf=dict(dropout_rate=0.1, positional_dropout_rate=0.1, attention_dropout_rate=0.1, **lm_spec["conf"])), f)
+            kw = dict(lm_train_config=lm_yaml, lm_file=None, lm_weight=lm_spec["weight"])
+        s2t = refbuild.build_reference(cfg, seed=0, beam_size=beam, ctc_weight=ctcw, maxlenratio=mlr, nbest=1, **kw)
+        s2t.asr_model.load_state_dict(weights["asr"] if "asr" in weights else weights, strict=True)   # same weights as the CUDA arm (parity check of the bench)
         s2t.asr_model.eval()
+        if lm_spec is not None:
+            s2t.beam_search.full_scorers["lm"].load_state_dict(weights["lm"], strict=True)
         run = lambda w: s2t(w.numpy())  # noqa: E731
     else:
         import oracle
 
+        if lm_spec is not None:
+            raise RuntimeError("the LM-fusion workload needs the real reference (oracle/_ref) on the CPU arm")
         o = oracle.OracleSpeech2Text(cfg, weights, beam_size=beam, ctc_weight=ctcw, maxlenratio=mlr, nbest=1)
         run = lambda w: o(w)  # noqa: E731
     outq.put(("ready", rank))
@@ -124,7 +157,7 @@ def _ref_worker(rank, cfg, wfile, beam, ctcw, mlr, inq, outq):
 class RefPool:
     """REF_WORKERS reference decoders; decode(waves) runs one utterance per worker concurrently and returns the wall time."""
 
-    def __init__(self, cfg, beam, ctcw, mlr, workers):
+    def __init__(self, cfg, beam, ctcw, mlr, workers, workload=None):
         import tempfile
 
         import torch.multiprocessing as mp
@@ -132,10 +165,11 @@ class RefPool:
         self.n = workers
         ctx = mp.get_context("spawn")
         self.wfile = os.path.join(tempfile.mkdtemp(prefix="espb_ref_"), "weights.pt")
-        torch.save(model_weights(cfg), self.wfile)
+        lm_spec, lmw = LM_FUSION.get(workload), lm_weights(workload, cfg["vocab"])
+        torch.save(model_weights(cfg) if lmw is None else {"asr": model_weights(cfg), "lm": lmw}, self.wfile)
         self.inq = [ctx.Queue() for _ in range(workers)]
         self.outq = ctx.Queue()
-        self.procs = [ctx.Process(target=_ref_worker, args=(r, cfg, self.wfile, beam, ctcw, mlr, self.inq[r], self.outq), daemon=True)
+        self.procs = [ctx.Process(target=_ref_worker, args=(r, cfg, self.wfile, beam, ctcw, mlr, self.inq[r], self.outq, lm_spec), daemon=True)
                       for r in range(workers)]
         for p in self.procs:
             p.start()
@@ -158,10 +192,11 @@ class RefPool:
             p.join(timeout=30)
 
 
-def ref_sample_desc(secs, mlr, workers, beam):
+def ref_sample_desc(secs, mlr, workers, beam, workload=None):
     return (f"{workers} utterance(s) of {secs} s decoded concurrently, one per process ({workers} processes x {REF_THREADS} torch threads of "
             f"{os.cpu_count()} host threads), each batch-1 through {'espnet2.bin.asr_inference.Speech2Text (oracle/_ref)' if ref_kind() == 'reference' else 'the oracle port'}: "
-            f"encoder + the full {int(-mlr)}-step joint beam-{beam} search, no extrapolation")
+            f"encoder + the full {int(-mlr)}-step joint beam-{beam} search"
+            + (f" with TransformerLM shallow fusion (lm_weight {LM_FUSION[workload]['weight']})" if workload in LM_FUSION else "") + ", no extrapolation")
 
 
 class ClockSampler:
@@ -231,7 +266,7 @@ def run_reference(args, rank, world):
     cfg, secs, batch, beam, ctcw, mlr = WORKLOADS[args.workload]
     workers = ref_workers()
     t_start = time.perf_counter()
-    pool = RefPool(cfg, beam, ctcw, mlr, workers)
+    pool = RefPool(cfg, beam, ctcw, mlr, workers, args.workload)
     warm = min(args.warmup, 1)
     waves = waveforms((warm + args.steps) * workers, secs * 16000)
     budget = float(os.environ.get("ESPB_REF_BUDGET_S", 330))
@@ -249,7 +284,7 @@ def run_reference(args, rank, world):
     done = len(walls)
     dt = sum(walls)
     ups = done * workers / dt
-    desc = ref_sample_desc(secs, mlr, workers, beam)
+    desc = ref_sample_desc(secs, mlr, workers, beam, args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": ups, "unit": "utterances/s", "n_gpus": args.gpus, "steps": done,
         "warmup": warm, "ms_per_step": 1000.0 * dt / done, "higher_is_better": True, "scaling": "weak",
@@ -354,7 +389,15 @@ def run_b200(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     cfg, secs, batch, beam, ctcw, mlr = WORKLOADS[args.workload]
     nsamp = secs * 16000
-    s2t = speech2text(cfg, model_weights(cfg), beam_size=beam, ctc_weight=ctcw, maxlenratio=mlr, nbest=1)
+    kw = {}
+    if args.workload in LM_FUSION:
+        import espnet_b200 as _eb
+
+        spec = LM_FUSION[args.workload]
+        lm = _eb.TransformerLM(cfg["vocab"], **spec["conf"])
+        lm.load_state_dict(lm_weights(args.workload, cfg["vocab"]), strict=True)
+        kw = dict(lm=lm, lm_weight=spec["weight"])
+    s2t = speech2text(cfg, model_weights(cfg), beam_size=beam, ctc_weight=ctcw, maxlenratio=mlr, nbest=1, **kw)
     host = waveforms(batch, nsamp, offset=rank * batch).pin_memory()      # utterances sharded by rank
     lens = torch.full((batch,), nsamp, dtype=torch.long)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -577,7 +620,9 @@ def run_b200(args, rank, local_rank, world):
         "config": {"workload": args.workload, "global_batch": world * batch, "utt_seconds": secs, "beam": beam, "ctc_weight": ctcw,
                    "maxlenratio": mlr, "vocab": cfg["vocab"], "parallelism": f"utterance-sharded x{world}", "l2": "flushed between steps (256 MiB write)",
                    "gemm": "tcgen05 kind::tf32 x3 (error-compensated fp32), mode " + ops.gemm_mode(), "attention": ops.attn_mode(),
-                   "wall_s_timed_region": wall},
+                   "wall_s_timed_region": wall,
+                   **({"lm": {"type": "TransformerLM", "weight": LM_FUSION[args.workload]["weight"], **LM_FUSION[args.workload]["conf"]},
+                       "decode_setup": "egs2/librispeech/asr1/conf/decode_asr.yaml:1-3 (beam 60, ctc 0.3, lm 0.6)"} if args.workload in LM_FUSION else {})},
         "e2e": {"value": e2e, "unit": "utterances/s", "h2d_bytes_per_step": batch * nsamp * 4,
                 "d2h_bytes_per_step": int(2 * 4 * 64 * batch * beam + 6 * 4 * batch * beam * 64), "ms_per_step": e2e_ms / args.steps,
                 "api": "Speech2Text.decode_stream (double-buffered pinned H2D)" + (" + batch_decode_sharded (all-gather of n-best records)" if world > 1 else ""),
@@ -602,14 +647,14 @@ def run_b200(args, rank, local_rank, world):
     print("[bench] gpu arm done: " + json.dumps(line), file=sys.stderr, flush=True)
     if args.cpu_baseline and world == 1:   # the host-core baseline is reported by the single-GPU run only
         workers = ref_workers()
-        n_par = 4                             # parity is checked on more utterances than the timed sample (those run concurrently, untimed)
-        pool = RefPool(cfg, beam, ctcw, mlr, max(workers, n_par))
+        n_par = 1 if args.workload in LM_FUSION else 4   # parity is checked on more utterances than the timed sample (those run concurrently, untimed)
+        pool = RefPool(cfg, beam, ctcw, mlr, max(workers, n_par), args.workload)
         wall, out = pool.decode([host[i] for i in range(workers)])      # the first `workers` utterances of this rank's batch, no warm-up
         _, more = pool.decode([host[workers + i] for i in range(n_par)])
         out = out + [(workers + i, dt, ys, sc) for i, dt, ys, sc in more]
         pool.close()
         line["cpu_baseline"] = {"value": workers / wall, "unit": "utterances/s", "cores": workers * REF_THREADS, "kind": ref_kind(),
-                                "sample": ref_sample_desc(secs, mlr, workers, beam) + "; one step, no warm-up"}
+                                "sample": ref_sample_desc(secs, mlr, workers, beam, args.workload) + "; one step, no warm-up"}
         # parity of the benchmarked configuration, enforced by the bench itself: the CUDA n-best of the same utterances (from the last timed
         # end-to-end step) against the reference CPU result -- identical token sequences, scores within rtol 2e-4
         eq, rel = True, 0.0
