@@ -40,6 +40,61 @@ __device__ __forceinline__ float epi_value(const EpiArgs& e, float acc, long lon
 }
 
 // ------------------------------------------------------------------ tensor-core kernel
+// Epilogue of one 32-column chunk of a 128-row 1-CTA tile (the thread owns row `row`, v[] holds its 32 accumulators): bias, activation,
+// alpha / residual, optional hi / lo split; 128-bit accesses when the layout allows.  Shared by the 1-CTA, multicast and split-K kernels.
+__device__ __forceinline__ void epi_store_chunk32(const EpiArgs& e, float (&v)[32], int row, bool row_ok, int col0, int N, bool vec_ok, bool r_vec_ok) {
+  float* crow = e.C + (long long)row * e.ldc;
+  if (!row_ok || col0 >= N) return;   // nothing to store for this lane / column chunk (tile overhang)
+  if (vec_ok && col0 + 32 <= N) {
+    // residual (may alias the output: x += ...) and bias are fetched up front with 128-bit loads, so the 8 loads are in flight
+    // together instead of one dependent load -> store round trip per element
+    float rres[32];
+    if (e.R && r_vec_ok) {
+      const float4* rp4 = reinterpret_cast<const float4*>(e.R + (long long)row * e.ldr + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float4 t = rp4[j]; rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rres[j] = e.R ? e.R[(long long)row * e.ldr + col0 + j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = v[j];
+      if (e.bias) x += __ldg(e.bias + col0 + j);
+      x = espb::apply_act_acc(x, e.act);
+      v[j] = fmaf(e.alpha, x, rres[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 o, l;
+      const float t0 = v[j], t1 = v[j + 1], t2 = v[j + 2], t3 = v[j + 3];
+      if (e.split_out) {
+        o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
+        l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
+        *reinterpret_cast<float4*>(crow + col0 + j) = o;
+        *reinterpret_cast<float4*>(crow + e.c_plane + col0 + j) = l;
+      } else {
+        o.x = t0; o.y = t1; o.z = t2; o.w = t3;
+        *reinterpret_cast<float4*>(crow + col0 + j) = o;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (col < N) {
+        const float t = epi_value(e, v[j], row, col);
+        if (e.split_out) {
+          const float h = espb::tf32_hi(t);
+          crow[col] = h; crow[e.c_plane + col] = espb::tf32_lo(t, h);
+        } else {
+          crow[col] = t;
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EspbGemmDesc p, int bxm, int bym, int axm, int aym) {
@@ -147,58 +202,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       float v[32];
       __syncwarp();
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      const int col0 = n0 + c * 32;
-      float* crow = e.C + (long long)row * e.ldc;
-      if (!row_ok || col0 >= p.N) {
-        // nothing to store for this lane / column chunk (tile overhang)
-      } else if (vec_ok && col0 + 32 <= p.N) {
-        // residual (may alias the output: x += ...) and bias are fetched up front with 128-bit loads, so the 8 loads are in flight
-        // together instead of one dependent load -> store round trip per element
-        float rres[32];
-        if (e.R && r_vec_ok) {
-          const float4* rp4 = reinterpret_cast<const float4*>(e.R + (long long)row * e.ldr + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 t = rp4[j]; rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rres[j] = e.R ? e.R[(long long)row * e.ldr + col0 + j] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = v[j];
-          if (e.bias) x += __ldg(e.bias + col0 + j);
-          x = espb::apply_act_acc(x, e.act);
-          v[j] = fmaf(e.alpha, x, rres[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o, l;
-          const float t0 = v[j], t1 = v[j + 1], t2 = v[j + 2], t3 = v[j + 3];
-          if (e.split_out) {
-            o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
-            l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
-            *reinterpret_cast<float4*>(crow + col0 + j) = o;
-            *reinterpret_cast<float4*>(crow + e.c_plane + col0 + j) = l;
-          } else {
-            o.x = t0; o.y = t1; o.z = t2; o.w = t3;
-            *reinterpret_cast<float4*>(crow + col0 + j) = o;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col < p.N) {
-            float t = epi_value(e, v[j], row, col);
-            if (e.split_out) {
-              float h = espb::tf32_hi(t);
-              crow[col] = h; crow[e.c_plane + col] = espb::tf32_lo(t, h);
-            } else {
-              crow[col] = t;
-            }
-          }
-        }
-      }
+      epi_store_chunk32(e, v, row, row_ok, n0 + c * 32, p.N, vec_ok, r_vec_ok);
     }
   }
   tcgen05_fence_before();
@@ -314,58 +318,7 @@ gemm_tf32x3_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       float v[32];
       __syncwarp();
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      const int col0 = n0 + c * 32;
-      float* crow = e.C + (long long)row * e.ldc;
-      if (!row_ok || col0 >= p.N) {
-        // nothing to store for this lane / column chunk (tile overhang)
-      } else if (vec_ok && col0 + 32 <= p.N) {
-        // residual (may alias the output: x += ...) and bias are fetched up front with 128-bit loads, so the 8 loads are in flight
-        // together instead of one dependent load -> store round trip per element
-        float rres[32];
-        if (e.R && r_vec_ok) {
-          const float4* rp4 = reinterpret_cast<const float4*>(e.R + (long long)row * e.ldr + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 t = rp4[j]; rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rres[j] = e.R ? e.R[(long long)row * e.ldr + col0 + j] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = v[j];
-          if (e.bias) x += __ldg(e.bias + col0 + j);
-          x = espb::apply_act_acc(x, e.act);
-          v[j] = fmaf(e.alpha, x, rres[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o, l;
-          const float t0 = v[j], t1 = v[j + 1], t2 = v[j + 2], t3 = v[j + 3];
-          if (e.split_out) {
-            o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
-            l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
-            *reinterpret_cast<float4*>(crow + col0 + j) = o;
-            *reinterpret_cast<float4*>(crow + e.c_plane + col0 + j) = l;
-          } else {
-            o.x = t0; o.y = t1; o.z = t2; o.w = t3;
-            *reinterpret_cast<float4*>(crow + col0 + j) = o;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col < p.N) {
-            float t = epi_value(e, v[j], row, col);
-            if (e.split_out) {
-              float h = espb::tf32_hi(t);
-              crow[col] = h; crow[e.c_plane + col] = espb::tf32_lo(t, h);
-            } else {
-              crow[col] = t;
-            }
-          }
-        }
-      }
+      epi_store_chunk32(e, v, row, row_ok, n0 + c * 32, p.N, vec_ok, r_vec_ok);
     }
   }
   tcgen05_fence_before();
@@ -506,56 +459,7 @@ gemm_tf32x3_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
         }
       }
-      const int col0 = n0 + c * 32;
-      float* crow = e.C + (long long)row * e.ldc;
-      if (!row_ok || col0 >= p.N) {
-        // tile overhang
-      } else if (vec_ok && col0 + 32 <= p.N) {
-        float rres[32];
-        if (e.R && r_vec_ok) {
-          const float4* rp4 = reinterpret_cast<const float4*>(e.R + (long long)row * e.ldr + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 t = rp4[j]; rres[4 * j] = t.x; rres[4 * j + 1] = t.y; rres[4 * j + 2] = t.z; rres[4 * j + 3] = t.w; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rres[j] = e.R ? e.R[(long long)row * e.ldr + col0 + j] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = v[j];
-          if (e.bias) x += __ldg(e.bias + col0 + j);
-          x = espb::apply_act_acc(x, e.act);
-          v[j] = fmaf(e.alpha, x, rres[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o, l;
-          const float t0 = v[j], t1 = v[j + 1], t2 = v[j + 2], t3 = v[j + 3];
-          if (e.split_out) {
-            o.x = espb::tf32_hi(t0); o.y = espb::tf32_hi(t1); o.z = espb::tf32_hi(t2); o.w = espb::tf32_hi(t3);
-            l.x = espb::tf32_lo(t0, o.x); l.y = espb::tf32_lo(t1, o.y); l.z = espb::tf32_lo(t2, o.z); l.w = espb::tf32_lo(t3, o.w);
-            *reinterpret_cast<float4*>(crow + col0 + j) = o;
-            *reinterpret_cast<float4*>(crow + e.c_plane + col0 + j) = l;
-          } else {
-            o.x = t0; o.y = t1; o.z = t2; o.w = t3;
-            *reinterpret_cast<float4*>(crow + col0 + j) = o;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col < p.N) {
-            float t = epi_value(e, v[j], row, col);
-            if (e.split_out) {
-              float h = espb::tf32_hi(t);
-              crow[col] = h; crow[e.c_plane + col] = espb::tf32_lo(t, h);
-            } else {
-              crow[col] = t;
-            }
-          }
-        }
-      }
+      epi_store_chunk32(e, v, row, row_ok, n0 + c * 32, p.N, vec_ok, r_vec_ok);
     }
   }
   tcgen05_fence_before();
