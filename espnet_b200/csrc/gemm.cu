@@ -484,6 +484,7 @@ constexpr int CHUNK_KB = 4;
 
 // rel-pos band (EspbGemmDesc::band_t): a tile of rows [m0, m0+bm) x columns [n0, n0+bn) is needed iff it intersects
 // { (m, n) : T-1-m <= n <= 2T-2-m }.
+__constant__ int c_band_blocks = 1;   // 0 (ESPB_GEMM_BAND_TILES_ONLY=1): skip whole tiles only, store every 32 x 32 block of a computed tile (A/B measurements)
 __device__ __forceinline__ bool band_skip(int T, int m0, int bm, int n0, int bn) {
   if (T <= 0) return false;
   return (n0 + bn - 1 < T - 1 - (m0 + bm - 1)) || (n0 > 2 * T - 2 - m0);
@@ -676,6 +677,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         for (int j = 0; j < CW / 32; ++j) {
           const int colb = n0 + half * CW + j * 32;
           if (row0 >= p.M || colb >= Ncols) continue;          // warp-uniform: block entirely outside the matrix
+          if (c_band_blocks && band_skip(p.band_t, row0, 32, colb, 32)) continue;  // rel-pos band product: a 32 x 32 block no (query, key) pair reaches is not stored
           if (PLAIN && row0 + 32 <= p.M && colb + 32 <= Ncols) {
             // interior block of a product without bias / residual / scaling (attention scores, context): straight-line transpose + stores,
             // no per-row or per-column predicates (the generic path below spends most of its issue slots on them)
@@ -771,6 +773,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         for (int j = 0; j < CW / 32; ++j) {
           const int colb = n0 + half * CW + j * 32;
           if (row0 >= p.M || colb >= Ncols) continue;
+          if (c_band_blocks && band_skip(p.band_t, row0, 32, colb, 32)) continue;
 #pragma unroll 1
           for (int hh = 0; hh < NH; ++hh) {
             __syncwarp();
@@ -911,6 +914,7 @@ int launch_tc2_ew(const CUtensorMap& tmA, const CUtensorMap& tmB, const EspbGemm
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (getenv("ESPB_GEMM_BAND_TILES_ONLY")) { const int zero = 0; cudaMemcpyToSymbol(c_band_blocks, &zero, sizeof(int)); }
     attr_set = true;
   }
   const long long tiles = (long long)((d.M + 255) / 256) * ((d.N + BN - 1) / BN) * d.nbx * d.nby;
