@@ -96,6 +96,37 @@ def test_streaming_speech2text_from_config_and_checkpoint_files(monkeypatch, tmp
         espnet_b200.BatchBeamSearchOnline({}, {}, 2, 10, 9, 9, time_sync=True)
 
 
+def test_streaming_cli_sim_chunk_length_writes_result_dir(monkeypatch, tmp_path):
+    """bin_asr_inference_streaming.inference (asr_inference_streaming.py:360-487): scp in, simulated chunks of --sim_chunk_length samples, the final
+    push's n-best out as {n}best_recog/{token,token_int,score}.  The block-synchronous search only depends on the encoder blocks, not on how the
+    samples were chunked, so the result equals the reference fixture's final n-best (pushed in different, uneven chunks there)."""
+    import emu_backend
+    import espnet_b200
+    from espnet_b200.bin_asr_inference_streaming import get_parser, inference
+
+    emu_backend.install_search(monkeypatch)
+    emu_backend.install_frontend(monkeypatch)
+    z = np.load(GOLD)
+    model, _ = _model(z, "cpu")
+    kw = json.loads(str(z["settings"]))["joint_pen_norep"]
+    s2t = espnet_b200.Speech2TextStreaming(model, device="cpu", **kw)
+    np.save(tmp_path / "utt1.npy", z["wave"])
+    (tmp_path / "wav.scp").write_text(f"utt1 {tmp_path / 'utt1.npy'}\n")
+    out = inference(str(tmp_path / "dec"), [(str(tmp_path / "wav.scp"), "speech", "sound")], nbest=kw["nbest"], sim_chunk_length=4000, speech2text=s2t)
+    last = len(z["pushes"]) - 1
+    n_ref = int(z[f"joint_pen_norep:{last}:n"])
+    assert len(out["utt1"]) == n_ref
+    lines = dict(ln.split(maxsplit=1) for ln in (tmp_path / "dec/1best_recog/token_int").read_text().splitlines())
+    assert lines["utt1"].split() == [str(t) for t in z[f"joint_pen_norep:{last}:0:token_int"].tolist()]
+    for j in range(n_ref):
+        assert out["utt1"][j][3].yseq.tolist() == z[f"joint_pen_norep:{last}:{j}:yseq"].tolist()
+        assert abs(float(out["utt1"][j][3].score) - float(z[f"joint_pen_norep:{last}:{j}:score"])) < 2e-3 + 2e-4 * abs(float(z[f"joint_pen_norep:{last}:{j}:score"]))
+    assert (tmp_path / f"dec/{n_ref}best_recog/score").exists()
+    a = get_parser().parse_args(["--output_dir", "o", "--data_path_and_name_and_type", "wav.scp,speech,sound", "--asr_train_config", "c", "--asr_model_file", "m",
+                                 "--sim_chunk_length", "640", "--disable_repetition_detection", "true"])
+    assert a.sim_chunk_length == 640 and a.disable_repetition_detection is True and a.ctc_weight == 0.5 and a.beam_size == 20
+
+
 @pytest.mark.gpu
 def test_streaming_beam_search_cuda_vs_reference_fixture():
     _run("cuda")
