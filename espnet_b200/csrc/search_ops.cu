@@ -522,6 +522,9 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* _
   }
 }
 
+#ifndef ESPB_SRC_ATTN_NW_DEFAULT
+#define ESPB_SRC_ATTN_NW_DEFAULT 4
+#endif
 // ---------------------------------------------------------------- cross-attention, single pass (d_k = 64, beam <= 16, any T)
 // Flash-decoding inside a block: K and V tiles of 64 frames stream TOGETHER through an S-deep cp.async ring (no [W][T] score buffer, so twice
 // the bytes are in flight per SM and T is unbounded); warp w owns frames 8w..8w+7 of every tile and keeps its own online-softmax state
@@ -529,11 +532,11 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_mma_kernel(const float* _
 //   scores  C[16 slots][8 frames] = Q (A, split once into registers / smem) x K^T (B): every K element is read and split once
 //   context O[16 slots][64]      += P (A = the C fragment re-used in place: the k index of the second product is simply a permutation of
 //                                   the warp's 8 frames, lane t4 holds frames 2 t4, 2 t4 + 1) x V (B rows picked with the same permutation)
-template <int S>
-__global__ void __launch_bounds__(256, 2) dec_src_attn_flash_kernel(const float* __restrict__ q, const float* __restrict__ kmem, const float* __restrict__ vmem,
+template <int S, int NW>   // NW warps per block, 8 NW frames per tile: NW = 4 -> four 57 KB blocks per SM, all U x H blocks of a 64 x 8 launch resident at once
+__global__ void __launch_bounds__(NW * 32, 16 / NW) dec_src_attn_flash_kernel(const float* __restrict__ q, const float* __restrict__ kmem, const float* __restrict__ vmem,
                                                                     int Tmax, const int* __restrict__ lens, int W, int D, int H,
                                                                     float* __restrict__ ctx, long long ctx_plane, int w0, int Wall) {
-  constexpr int DK = 64, QST = 68, ST = 68, TR = 64, TILE_F = TR * ST, STAGE_F = 2 * TILE_F;
+  constexpr int DK = 64, QST = 68, ST = 68, TR = 8 * NW, TILE_F = TR * ST, STAGE_F = 2 * TILE_F;
   extern __shared__ float sm[];  // q lo [16][68] | ring [S][K [64][68] | V [64][68]] (reused for the cross-warp merge)
   espb::pdl_trigger();
   espb::pdl_wait();
@@ -551,8 +554,8 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_flash_kernel(const float*
       const int tb = i * TR;
       float* dst = ring + (i % S) * STAGE_F;
 #pragma unroll
-      for (int j = threadIdx.x; j < 2 * TR * 16; j += 256) {
-        const int isv = j >> 10, rr = (j >> 4) & 63, cc = j & 15;
+      for (int j = threadIdx.x; j < 2 * TR * 16; j += NW * 32) {
+        const int isv = j / (TR * 16), rr = (j >> 4) % TR, cc = j & 15;
         const bool ok = tb + rr < T;      // frames past the utterance are zero-filled (src-size 0)
         cp_async16_zfill(dst + isv * TILE_F + rr * ST + cc * 4, (isv ? vb : kb) + (ok ? (long long)(tb + rr) * 16 + cc : 0), ok ? 16 : 0);
       }
@@ -634,9 +637,9 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_flash_kernel(const float*
   }
   cp_async_wait<0>();
   __syncthreads();
-  // ---- merge of the eight warps: red[warp][slot 16][66] = (O[64], m, l) in the ring
+  // ---- merge of the NW warps: red[warp][slot 16][66] = (O[64], m, l) in the ring
   float* red = ring;
-  static_assert(S * STAGE_F >= 8 * 16 * 66, "merge scratch must fit in the ring");
+  static_assert(S * STAGE_F >= NW * 16 * 66, "merge scratch must fit in the ring");
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
 #pragma unroll
@@ -655,10 +658,10 @@ __global__ void __launch_bounds__(256, 2) dec_src_attn_flash_kernel(const float*
     const int w = i / DK, d = i % DK;
     float M = -INFINITY;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) M = fmaxf(M, red[((long long)ww * 16 + w) * 66 + 64]);
+    for (int ww = 0; ww < NW; ++ww) M = fmaxf(M, red[((long long)ww * 16 + w) * 66 + 64]);
     float L = 0.f, a = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) {
+    for (int ww = 0; ww < NW; ++ww) {
       const float* r = red + ((long long)ww * 16 + w) * 66;
       const float e = expf(r[64] - M);      // a warp without frames: exp(-inf) = 0
       L = fmaf(r[65], e, L);
@@ -1155,8 +1158,12 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
     if (dk == 64 && !getenv("ESPNET_B200_SRC_ATTN_FFMA") && !getenv("ESPNET_B200_SRC_ATTN_TWOPASS")) {
       // single-pass kernel: 3 stages of (K, V) tiles = 112 KB -> two blocks per SM, 128 KB of loads in flight per SM
       using FlashFn = void (*)(const float*, const float*, const float*, int, const int*, int, int, int, float*, long long, int, int);
-      const FlashFn fn = dec_src_attn_flash_kernel<3>;
-      const size_t smem = (16 * 68 + 3 * 2 * 64 * 68) * sizeof(float);
+      // NW = 4 (default): four 57 KB blocks per SM, 592 resident -- a 64-utterance x 8-head launch is one wave; NW = 8 (ESPB_SRC_ATTN_NW=8, the
+      // first version): two 112 KB blocks per SM, 296 resident = 1.73 waves.  Same bytes in flight per SM; measured 80.9 -> 74.9 us per launch.
+      static int nw = 0;
+      if (!nw) { const char* e = getenv("ESPB_SRC_ATTN_NW"); nw = (e && e[0] == '8') ? 8 : (e && e[0] == '4') ? 4 : ESPB_SRC_ATTN_NW_DEFAULT; }
+      const FlashFn fn = (nw == 4) ? dec_src_attn_flash_kernel<3, 4> : dec_src_attn_flash_kernel<3, 8>;
+      const size_t smem = (16 * 68 + 3 * 2 * 8 * nw * 68) * sizeof(float);
       static bool attr = false;
       if (!attr) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -1164,7 +1171,7 @@ int espb_dec_src_attn_f32(const float* q, const float* kmem, const float* vmem, 
         }
         attr = true;
       }
-      espb::launch_pdl(fn, dim3(U * H), dim3(256), smem, stream, q, kmem, vmem, Tmax, lens, Wg, D, H, ctx, ctx_plane, w0, W);
+      espb::launch_pdl(fn, dim3(U * H), dim3(nw * 32), smem, stream, q, kmem, vmem, Tmax, lens, Wg, D, H, ctx, ctx_plane, w0, W);
       ESPB_CHECK_LAUNCH();
       continue;
     }
