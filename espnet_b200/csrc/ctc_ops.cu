@@ -1,6 +1,8 @@
 // CTC head kernels: row-wise log-softmax / argmax over the vocabulary and on-device greedy collapse.
 // Reference: espnet2/asr/ctc.py:197-215 (log_softmax, argmax), espnet2/bin/asr_inference.py:574-575 and
 // espnet2/bin/s2t_inference_ctc.py:630-632 (unique_consecutive + drop blank).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -19,6 +21,34 @@ __global__ void __launch_bounds__(256) log_softmax_rows_kernel(float* __restrict
   s = espb::block_sum(s, red);
   const float lse = mx + logf(s);
   for (int i = threadIdx.x; i < V; i += blockDim.x) r[i] = r[i] - lse;
+}
+
+// Same result (same per-thread summation order), one global read: thread t keeps x[t + 256 k], k < NV, in registers (V <= 256 NV).
+template <int NV>
+__global__ void __launch_bounds__(256) log_softmax_rows_reg_kernel(float* __restrict__ x, long long ld, int V) {
+  espb::pdl_trigger();
+  espb::pdl_wait();
+  __shared__ float red[33];
+  float* r = x + (long long)blockIdx.x * ld;
+  float v[NV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = threadIdx.x + k * 256;
+    v[k] = (i < V) ? r[i] : -INFINITY;
+    mx = fmaxf(mx, v[k]);
+  }
+  mx = espb::block_max(mx, red);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) if (threadIdx.x + k * 256 < V) s += expf(v[k] - mx);
+  s = espb::block_sum(s, red);
+  const float lse = mx + logf(s);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = threadIdx.x + k * 256;
+    if (i < V) r[i] = v[k] - lse;
+  }
 }
 
 // argmax of each row (first index on ties, as torch.argmax on CPU). One warp per row.
@@ -69,7 +99,12 @@ extern "C" {
 
 int espb_log_softmax_rows_f32(float* x, long long rows, long long ld, int V, cudaStream_t stream) {
   if (rows <= 0) return ESPB_OK;
-  espb::launch_pdl(log_softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, stream, x, ld, V);
+  static int three_pass = -1;
+  if (three_pass < 0) three_pass = getenv("ESPB_LOGSOFTMAX_3PASS") ? 1 : 0;
+  if (!three_pass && V <= 256 * 8) espb::launch_pdl(log_softmax_rows_reg_kernel<8>, dim3((unsigned)rows), dim3(256), 0, stream, x, ld, V);
+  else if (!three_pass && V <= 256 * 20) espb::launch_pdl(log_softmax_rows_reg_kernel<20>, dim3((unsigned)rows), dim3(256), 0, stream, x, ld, V);
+  else if (!three_pass && V <= 256 * 32) espb::launch_pdl(log_softmax_rows_reg_kernel<32>, dim3((unsigned)rows), dim3(256), 0, stream, x, ld, V);
+  else espb::launch_pdl(log_softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, stream, x, ld, V);
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }

@@ -134,3 +134,10 @@ if which in ("ac", "all"):
     timeit(f"q_u.k^T GEMM T{T} x T{T} x {dk}, {B * H} problems ({2.0 * B * H * T * T * dk / 1e12:.3f} TFLOP algorithmic)",
            lambda: ops.gemm(T, T, dk, qu, M * D, D, qkv, M * 3 * D, 3 * D, ac, Tp, nbx=H, nby=B, sa=(dk, T * D), sb=(dk, T * 3 * D),
                             sc=(T * Tp, H * T * Tp), b_off=D), alg)
+
+if which in ("logsoftmax", "all"):
+    # decode-step shape (640 hypotheses x V 5000) and the encoder-side CTC posteriors (64 x 937 frames); ESPB_LOGSOFTMAX_3PASS=1 = the first kernel
+    for rows in (640, 64 * 937):
+        x = torch.randn(rows, 5000, device=dev)
+        timeit(f"log_softmax_rows {rows} x 5000", lambda: call("espb_log_softmax_rows_f32", ptr(x), rows, 5000, 5000), 2 * rows * 5000 * 4)
+        del x
