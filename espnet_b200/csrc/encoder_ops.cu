@@ -365,6 +365,60 @@ __global__ void __launch_bounds__(256) glu_dwconv_bn_swish_kernel(const float* _
   }
 }
 
+// Same arithmetic (per output the same fmaf chain over k = 0..K-1, so bit-identical results), sliding window in registers: a thread owns one
+// channel and DW_RUN consecutive frames, reads each of the DW_RUN + K - 1 GLU'd inputs of its column once from shared memory and feeds it to the
+// up to K outputs it belongs to -- 2.9 shared-memory loads per output instead of 2 K (the first kernel is LDS-bound: 62 loads per output at K = 31).
+constexpr int DW_RUN = 16;
+template <int K>
+__global__ void __launch_bounds__(256) glu_dwconv_bn_swish_win_kernel(const float* __restrict__ y, int Tmax, int C, const int* __restrict__ lens,
+                                                                      const float* __restrict__ dw_w /*[C][K]*/, const float* __restrict__ dw_b,
+                                                                      const float* __restrict__ bn_a, const float* __restrict__ bn_b,
+                                                                      float* __restrict__ out, long long out_plane) {
+  static_assert(DW_TT == 4 * DW_RUN && DW_CC == 64, "256 threads = 64 channels x 4 runs of DW_RUN frames");
+  extern __shared__ float sm[];  // [(DW_TT + K - 1)][DW_CC] GLU'd tile
+  const int b = blockIdx.z, t0 = blockIdx.x * DW_TT, c0 = blockIdx.y * DW_CC;
+  const int len = lens[b];
+  constexpr int pad = (K - 1) / 2, rows = DW_TT + K - 1;
+  for (int i = threadIdx.x; i < rows * DW_CC; i += blockDim.x) {
+    const int r = i / DW_CC, c = c0 + (i % DW_CC), t = t0 - pad + r;
+    float v = 0.f;
+    if (t >= 0 && t < len && c < C) {
+      const float* p = y + ((long long)b * Tmax + t) * 2 * C;
+      const float a = p[c], g = p[C + c];
+      v = a * (1.f / (1.f + expf(-g)));
+    }
+    sm[i] = v;
+  }
+  __syncthreads();
+  const int cl = threadIdx.x & 63, run = threadIdx.x >> 6, c = c0 + cl;
+  if (c >= C) return;
+  float w[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) w[k] = __ldg(dw_w + (long long)c * K + k);
+  float acc[DW_RUN];
+#pragma unroll
+  for (int o = 0; o < DW_RUN; ++o) acc[o] = 0.f;
+  const float* col = sm + (run * DW_RUN) * DW_CC + cl;
+#pragma unroll
+  for (int r = 0; r < DW_RUN + K - 1; ++r) {
+    const float x = col[r * DW_CC];
+#pragma unroll
+    for (int o = 0; o < DW_RUN; ++o) {
+      if (r - o >= 0 && r - o < K) acc[o] = fmaf(x, w[r - o], acc[o]);   // resolved at compile time: input r is tap r - o of output o
+    }
+  }
+  const float db = dw_b[c], ba = bn_a[c], bb = bn_b[c];
+#pragma unroll
+  for (int o = 0; o < DW_RUN; ++o) {
+    const int t = t0 + run * DW_RUN + o;
+    if (t >= Tmax) break;
+    float z = (acc[o] + db) * ba + bb;
+    z = espb::swish_acc(z);
+    if (t >= len) z = 0.f;
+    store_split(out + ((long long)b * Tmax + t) * C + c, out_plane, z);
+  }
+}
+
 // x[b, t >= len_b, :] = 0 for plain and split buffers (keeps padded rows finite).
 __global__ void zero_pad_rows_kernel(float* __restrict__ x, int Tmax, int D, const int* __restrict__ lens, long long plane, int nplanes) {
   const int b = blockIdx.y;
@@ -567,8 +621,17 @@ int espb_glu_dwconv_bn_swish_f32(const float* y, int B, int Tmax, int C, const i
                                  const float* bn_a, const float* bn_b, float* out, long long out_plane, cudaStream_t stream) {
   if (K < 1 || (K & 1) == 0 || K > 127) { espb_set_error("dwconv: kernel size must be odd and <= 127"); return ESPB_ERR_ARG; }
   dim3 grid((Tmax + DW_TT - 1) / DW_TT, (C + DW_CC - 1) / DW_CC, B);
-  size_t smem = ((size_t)(DW_TT + K - 1) * DW_CC + (size_t)DW_CC * K) * sizeof(float);
-  glu_dwconv_bn_swish_kernel<<<grid, 256, smem, stream>>>(y, Tmax, C, lens, dw_w, dw_b, K, bn_a, bn_b, out, out_plane);
+  static int v1 = -1;
+  if (v1 < 0) v1 = getenv("ESPB_DWCONV_V1") ? 1 : 0;
+  const size_t smem_win = (size_t)(DW_TT + K - 1) * DW_CC * sizeof(float);
+  if (!v1 && K == 31) {
+    glu_dwconv_bn_swish_win_kernel<31><<<grid, 256, smem_win, stream>>>(y, Tmax, C, lens, dw_w, dw_b, bn_a, bn_b, out, out_plane);
+  } else if (!v1 && K == 15) {
+    glu_dwconv_bn_swish_win_kernel<15><<<grid, 256, smem_win, stream>>>(y, Tmax, C, lens, dw_w, dw_b, bn_a, bn_b, out, out_plane);
+  } else {
+    const size_t smem = ((size_t)(DW_TT + K - 1) * DW_CC + (size_t)DW_CC * K) * sizeof(float);
+    glu_dwconv_bn_swish_kernel<<<grid, 256, smem, stream>>>(y, Tmax, C, lens, dw_w, dw_b, K, bn_a, bn_b, out, out_plane);
+  }
   ESPB_CHECK_LAUNCH();
   return ESPB_OK;
 }
