@@ -772,10 +772,15 @@ __device__ __forceinline__ float ctc_log_psi_warp(const float* __restrict__ x, l
   const int start = max(out_len, 1);
   const bool same = (c == last);
   float m = -INFINITY, ssum = 0.f;   // per-lane streaming log-sum-exp, merged across the warp at the end
-  for (int t = start + lane; t < T; t += 32) {
-    const float e = ctc_phi(rp, t - 1, same) + __ldg(x + t * st_t + c * st_c);
-    if (e > m) { ssum = ssum * expf(m - e) + 1.f; m = e; } else { ssum += expf(e - m); }
+  const float* xc = x + c * st_c;
+  auto term = [&](int t) { return ctc_phi(rp, t - 1, same) + __ldg(xc + t * st_t); };
+  auto fold = [&](float e) { if (e > m) { ssum = ssum * expf(m - e) + 1.f; m = e; } else { ssum += expf(e - m); } };
+  int t = start + lane;
+  for (; t + 96 < T; t += 128) {     // four frames per lane at a time: the eight loads are issued together, the folds keep their order
+    const float e0 = term(t), e1 = term(t + 32), e2 = term(t + 64), e3 = term(t + 96);
+    fold(e0); fold(e1); fold(e2); fold(e3);
   }
+  for (; t < T; t += 32) fold(term(t));
   if (lane == 0) {   // the r[start-1,0] term
     const float r0 = (out_len == 0) ? x[c * st_c] : LOGZERO;
     if (r0 > m) { ssum = ssum * expf(m - r0) + 1.f; m = r0; } else { ssum += expf(r0 - m); }
