@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int NFFT = 512, HOP = 128, NBIN = 257, NC = 256;  // NC: complex points of the packed FFT
+constexpr int NFFT = 512, HOP = 128, NC = 256;  // NC: complex points of the packed FFT
 constexpr int WARPS = 4, FRAMES_PER_WARP = 8, FRAMES_PER_BLOCK = WARPS * FRAMES_PER_WARP;
 constexpr int SEG = (FRAMES_PER_BLOCK - 1) * HOP + NFFT;  // samples a block touches (with overlap)
 

@@ -665,7 +665,7 @@ gemm_tf32x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const long long ldc = ea.ldc, ldr = ea.ldr, cpl = ea.c_plane;
       const int Ncols = p.N;
       const float alpha = ea.alpha;
-      const bool split = SPLIT, has_r = ea.R != nullptr;
+      const bool has_r = ea.R != nullptr;
       float* const crow0 = ea.C + (long long)(row0 + rsub) * ldc;
       const float* const rrow0 = has_r ? ea.R + (long long)(row0 + rsub) * ldr : nullptr;
       float* const wrow = xp + (lane & (XR - 1)) * 36;
