@@ -30,8 +30,8 @@ WORKLOADS = {
     "conformer_large_joint_64x30s": (dict(d_model=512, heads=8, ff=2048, enc_layers=12, dec_layers=6, vocab=5000, kernel=31), 30, 64, 10, 0.3, -64.0),
     "conformer_large_joint_32x15s": (dict(d_model=512, heads=8, ff=2048, enc_layers=12, dec_layers=6, vocab=5000, kernel=31), 15, 32, 10, 0.3, -64.0),
     "conformer_4l256_joint_8x5s": (dict(d_model=256, heads=4, ff=2048, enc_layers=4, dec_layers=2, vocab=5000, kernel=31), 5, 8, 10, 0.3, -16.0),
-    # next scope row (SURVEY.md 8f-1 / BASELINE configs[4]): Transformer 24L/1024d/16h enc + 6L dec, attention-only beam 5.  Not a bench line of
-    # this round (the TransformerEncoder CUDA path is still opt-in in the tests); 64 utterances per GPU keep the conv1 planes within HBM.
+    # next scope row (SURVEY.md 8f-1 / BASELINE configs[4]): Transformer 24L/1024d/16h enc + 6L dec, attention-only beam 5; 64 utterances per GPU
+    # keep the conv1 planes within HBM (measured line: profiles/r02_bench_transformer_24l1024_att_64x30s_n1.json).
     "transformer_24l1024_att_64x30s": (dict(d_model=1024, heads=16, ff=4096, enc_layers=24, dec_layers=6, vocab=5000, encoder="transformer"),
                                        30, 64, 5, 0.0, -64.0),
 }

@@ -4,8 +4,8 @@ Conformer path (conv1 / implicit-GEMM conv2 / tcgen05 3xTF32 GEMMs / LayerNorm) 
 
 Reference: espnet2/asr/encoder/transformer_encoder.py:43-299, legacy/nets/pytorch_backend/transformer/encoder_layer.py:65-126,
 attention.py:77-151,262-265 (default branch), embedding.py:38-95 (PositionalEncoding), subsampling.py:397-474.
-STATUS: the CPU oracle (oracle/transformer_encoder.py) is pinned to the reference; the CUDA path below has not been run on a B200 yet --
-its parity test (tests/test_gpu_zz_next.py) is opt-in (ESPB_TEST_NEXT=1) until it has.
+Parity: tests/test_gpu_zz_next.py (reference fixture layer by layer, ragged batch, whole Speech2Text) and tests/test_host_logic_emulated.py; self-attention
+is the fused tcgen05 kernel without the rel-pos term (csrc/attention.cu) at d_k = 64.  Measured: bench.py --workload transformer_24l1024_att_64x30s.
 """
 import math
 from typing import List, Optional, Tuple
