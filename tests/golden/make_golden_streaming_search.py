@@ -49,6 +49,7 @@ SETTINGS = {
     "ctc_only": dict(beam_size=3, ctc_weight=1.0, nbest=2),
     "att_heavy_maxlen": dict(beam_size=2, ctc_weight=0.1, maxlenratio=0.2, nbest=2),
     "joint_lm": dict(beam_size=3, ctc_weight=0.3, lm_weight=0.5, nbest=2),       # + TransformerLM shallow fusion (lm_train_config)
+    "joint_normlen_minlen": dict(beam_size=3, ctc_weight=0.4, normalize_length=True, minlenratio=0.3, maxlenratio=0.6, penalty=0.2, nbest=3),
 }
 wave = refbuild.waveform(7, 52000)
 pushes = [8000, 640, 640, 9000, 12000, 3000, 18720]

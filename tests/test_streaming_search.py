@@ -58,7 +58,7 @@ def _run(device, names=None, n_streams=1):
                         assert abs(float(v) - r) <= 2e-4 * abs(r) + 2e-3, (key, k, float(v), r)
 
 
-@pytest.mark.parametrize("name", ["joint", "joint_pen_norep", "ctc_only", "att_heavy_maxlen", "joint_lm"])
+@pytest.mark.parametrize("name", ["joint", "joint_pen_norep", "ctc_only", "att_heavy_maxlen", "joint_lm", "joint_normlen_minlen"])
 def test_streaming_beam_search_host_logic_vs_reference_fixture(monkeypatch, name):
     import emu_backend
 
