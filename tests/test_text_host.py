@@ -136,3 +136,60 @@ def test_result_dir_writer_and_scp_reader(tmp_path):
     assert [k for k, _ in iter_scp(str(tmp_path / "wav.scp"), None, rank=1, world=2)] == ["u2"]
     np.testing.assert_allclose(read_sound(str(tmp_path / "a.wav")), x.astype(np.float32) / 32768.0)
     assert read_sound(str(tmp_path / "b.npy")).shape == (10,)
+
+
+def test_cli_inference_batching_writer_and_placeholder_with_a_stub_engine(tmp_path):
+    """bin_asr_inference.inference host logic (asr_inference.py:824-906) without a device: scp / key-file reading, --batch_size grouping, the
+    per-utterance retry when a batch holds a too-short utterance and the reference's placeholder hypothesis, the {n}best_recog/{token,token_int,score,text}
+    files.  The engine is a stub with Speech2Text's batch_decode / __call__ contract."""
+    import wave as wavmod
+
+    import numpy as np
+    import torch
+
+    from espnet_b200 import Hypothesis, TooShortUttError
+    from espnet_b200.bin_asr_inference import inference, iter_scp, read_sound
+
+    class Engine:
+        calls = []
+
+        def _one(self, w):
+            if len(w) < 1000:
+                raise TooShortUttError("too short", len(w), 1000)
+            n = len(w) // 1000
+            hyp = Hypothesis(yseq=torch.tensor([9] + list(range(3, 3 + n)) + [9]), score=torch.tensor(-float(n)))
+            return [(f"text{n}", [f"t{i}" for i in range(n)], list(range(3, 3 + n)), hyp), (None, ["x"], [4], hyp)]
+
+        def batch_decode(self, waves):
+            self.calls.append(len(waves))
+            return [self._one(w) for w in waves]
+
+        def __call__(self, w):
+            return self._one(w)
+
+    lens = {"a": 3000, "b": 500, "c": 5000, "d": 2000, "e": 4000}
+    lines = []
+    for k, n in lens.items():
+        pcm = (np.arange(n) % 100).astype("<i2")
+        with wavmod.open(str(tmp_path / f"{k}.wav"), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(pcm.tobytes())
+        lines.append(f"{k} {tmp_path / (k + '.wav')}")
+    (tmp_path / "wav.scp").write_text("\n".join(lines) + "\n")
+    (tmp_path / "keys").write_text("a\nb\nc\ne\n")
+    assert [k for k, _ in iter_scp(str(tmp_path / "wav.scp"), str(tmp_path / "keys"))] == ["a", "b", "c", "e"]
+    assert [k for k, _ in iter_scp(str(tmp_path / "wav.scp"), None, rank=1, world=2)] == ["b", "d"]
+    x = read_sound(str(tmp_path / "a.wav"))
+    assert x.dtype == np.float32 and len(x) == 3000 and abs(float(x[5]) - 5 / 32768.0) < 1e-9
+    eng = Engine()
+    out = inference(str(tmp_path / "dec"), [(str(tmp_path / "wav.scp"), "speech", "sound")], key_file=str(tmp_path / "keys"), batch_size=3, nbest=2,
+                    speech2text=eng)
+    assert eng.calls == [3, 1] and list(out) == ["a", "b", "c", "e"]            # one batch of three (holding the short one), then the rest
+    read = lambda p: dict((ln.split(maxsplit=1) + [""])[:2] for ln in (tmp_path / "dec" / p).read_text().splitlines())  # noqa: E731
+    tok, txt, sc = read("1best_recog/token_int"), read("1best_recog/text"), read("1best_recog/score")
+    assert tok["a"].split() == ["3", "4", "5"] and tok["b"].strip() == "2" and txt["c"].strip() == "text5" and float(sc["e"]) == -4.0
+    assert read("1best_recog/token")["b"].strip() == "<space>" and float(sc["b"]) == 0.0        # the placeholder of asr_inference.py:850-856
+    assert list(read("2best_recog/text")) == ["b"] and read("2best_recog/token")["a"].strip() == "x"    # text is None for the stub's 2nd best; the placeholder has one
+    import pytest
+
+    with pytest.raises(RuntimeError):
+        inference(str(tmp_path / "dec2"), [(str(tmp_path / "wav.scp"), "speech", "sound")], ngpu=0, speech2text=eng)
